@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- fused env-steps/s (plant + P/PI prior + float32 obs + residual actor) on N B200s.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                 # this repo's CUDA path (default)
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1  # the reference algorithm on the host CPU cores
+
+One bench "step" = one fused-rollout launch: every env of the shard advances T=200 env steps (one full
+episode of NonLinearWaterTankChangingParamUniformGoalIntegrator-SquareDistance-v2 with the Modular-256 residual
+actor, Philox process + exploration noise, replay rows written to HBM, in-kernel auto-reset with ensemble
+resampling).  Workload = BASELINE.json configs[2] ("1M-env water-tank ensemble rollout ... on 1 B200");
+for N > 1 each rank owns its own 2^20 envs (weak scaling, envs sharded by global env id, no data-path
+collective; one NCCL all-reduce of the 8-double episode statistics per step).
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "fused env-steps/sec (plant+PI+actor)"
+UNIT = "env-steps/s"
+WORKLOAD = "1M-env water-tank ensemble rollout, fused step+PI+actor (configs[2])"
+
+FLOPS_PER_STEP = {("modular", 256, 4): 264704, ("modular", 128, 3): 66560}  # 2 x weights, SURVEY 8a d4
+TANH_PER_STEP = {("modular", 256, 4): 1025, ("modular", 128, 3): 513}
+WT_STEP_BYTES_F32 = 57   # 36 B read + 21 B written per env-step, SoA fp32
+PH_STEP_BYTES_F32 = 53
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
+    p.add_argument("--T", type=int, default=200, help="env steps per launch (one episode)")
+    p.add_argument("--net-dim", type=int, default=256)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-aux", action="store_true", help="skip the stand-alone step-kernel roofline measurements")
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]), tf_sust=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    sm_max=float(d.get("sm_max_mhz", 1965.0)), src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, sm_max=1965.0, src="fallback (B200_PROFILING.md)")
+
+
+def actor_state_dict(H, S, seed=0):
+    """Modular actor at torch's default init scale; the last layer is N(0, 0.1^2) so that the MLP is not a numerical
+    no-op (the reference zero-initialises it, which would make every product zero)."""
+    rng = np.random.default_rng(seed)
+
+    def lin(o, i):
+        b = 1.0 / np.sqrt(i)
+        return rng.uniform(-b, b, (o, i)).astype(np.float32), rng.uniform(-b, b, o).astype(np.float32)
+    sd = {}
+    for name, o, i in [("other_net.0", H, S - 1), ("other_net.2", H // 2, H), ("integrator_net.0", H, 1),
+                       ("integrator_net.2", H // 2, H), ("net.0", H, H), ("net.2", 1, H)]:
+        sd[name + ".weight"], sd[name + ".bias"] = lin(o, i)
+    sd["net.2.weight"] = rng.normal(0, 0.1, (1, H)).astype(np.float32)
+    sd["a_std_log"] = np.array([[-0.5]], np.float32)
+    return sd
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.power = [], set(), []
+        self.sm_max = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+             0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.NAMES.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline(H, S, T, seconds, sd):
+    """The oracle (C restatement of the reference loop: fp64 plant + fp32 actor, oracle/pime_oracle.c) on all host
+    cores: one thread per core, each running explore-style rollouts on its own slice of envs (ctypes releases the GIL)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pime_oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    per = 16  # envs per thread per chunk: 16 x 200 steps x 265 kFLOP = 0.85 GFLOP per chunk
+    acfg = O.ActorCfg(kind=1, state_dim=S, mid_dim=H, integrator_dim=1)
+    params = O.pack_actor_params(sd, 1)
+    cfg = O.wt_cfg(reward_type="square_distance")
+    priorK = -np.array([0.0, 0.4, -0.4, 0.0])
+    counts = [0] * cores
+    deadline = [0.0]
+
+    def work(tid):
+        rng = np.random.default_rng(1000 + tid)
+        while time.perf_counter() < deadline[0]:
+            h1, h2, r = rng.uniform(0, 10, per), rng.uniform(0, 10, per), rng.uniform(0, 10, per)
+            a1, a2, Kp = rng.uniform(0.0015, 0.0024, per), rng.uniform(0.0015, 0.0024, per), rng.uniform(0.07, 0.17, per)
+            I, t = np.zeros(per), np.zeros(per, np.int32)
+            eps = rng.standard_normal((T, per)).astype(np.float32)
+            pn1, pn2 = rng.normal(0, 0.01, (T, per)), rng.normal(0, 0.01, (T, per))
+            O.wt_rollout(cfg, acfg, params, -0.5, priorK, 1, 0, False, T, h1, h2, r, I, t, a1, a2, Kp, eps=eps, pn1=pn1, pn2=pn2)
+            counts[tid] += per * T
+    # warm-up (library load, page-in)
+    deadline[0] = time.perf_counter() + 0.5
+    work(0)
+    counts[0] = 0
+    t0 = time.perf_counter()
+    deadline[0] = t0 + seconds
+    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    dt = time.perf_counter() - t0
+    total = sum(counts)
+    return {"value": total / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{total} env-steps ({total // T} episodes of T={T}, WT-Integrator + Modular-{H} actor, fp64 plant / fp32 actor, "
+                      f"C oracle, {cores} threads) in {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    H, S, T = args.net_dim, 4, args.T
+    sd = actor_state_dict(H, S)
+    vals = []
+    for _ in range(max(1, args.warmup)):
+        cpu_baseline(H, S, T, 1.0, sd)
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(max(1, args.steps)):
+        last = cpu_baseline(H, S, T, max(2.0, min(args.cpu_seconds, 60.0 / max(1, args.steps))), sd)
+        vals.append(last["value"])
+    v = float(np.mean(vals))
+    last["value"] = v
+    per_step_envsteps = v * (time.perf_counter() - t0) / max(1, args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * (time.perf_counter() - t0) / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 plant / f32 actor",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs, "T": T, "actor": f"ResidualIntegratorModularPPO-{H}",
+                       "note": "reference algorithm (C port of the numpy/torch loop) on all host cores; each step is a bounded "
+                               f"sample (~{per_step_envsteps:.3g} env-steps) of the workload"},
+            "cpu_baseline": last,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the pime_b200 hot path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import pime_b200.vec as V
+
+    pk = peaks()
+    n, T, H, S = args.envs, args.T, args.net_dim, 4
+    K = np.array([0.0, 0.4, -0.4, 0.0])
+    sd = actor_state_dict(H, S)
+    actor = V.ActorPack("modular", S, H, 1).update(sd)
+    env = V.WaterTankVec(n, dtype=torch.float32, obs_mode="integrator", reward_type="square_distance", noise_scale=0.01,
+                         seed=0, env_offset=rank * n)
+    env.reset()
+    bs = torch.empty((T, n, S), dtype=torch.float32, device="cuda")
+    bo = torch.empty((T, n, 4), dtype=torch.float32, device="cuda")
+    stats = torch.zeros(8, dtype=torch.float64, device="cuda")
+
+    def step():
+        stats.zero_()
+        env.rollout(T, -K, actor=actor, auto_reset=True, replay=(bs, bo), stats=stats, gamma=0.99)
+        if world > 1:
+            dist.all_reduce(stats)  # episode-return statistics of the whole job (the path's only exchange)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = float(tmax.item())
+    value = world * n * T * args.steps / (ms_total * 1e-3)
+    st = stats.cpu().numpy()
+    env.check_status()
+
+    # ---- e2e: the host-buffer API call (pinned host state in, ep_return out), H2D/D2H inside the timed region
+    host = {k: getattr(env, k).detach().cpu().pin_memory() for k in ("h1", "h2", "r", "I", "a1", "a2", "Kp")}
+    host["t"] = torch.zeros(n, dtype=torch.int32).pin_memory()
+    host["episode"] = env.episode.detach().cpu().pin_memory()
+    ret_host = torch.empty(n, dtype=torch.float32).pin_memory()
+    flat_host = actor.flat.detach().cpu().pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host.values()) + flat_host.numel() * 4
+    d2h = ret_host.numel() * 4 + 4 * n * 4 + 64
+
+    def e2e_step():
+        actor.flat.copy_(flat_host, non_blocking=True)           # actor weights from the (host-side) learner
+        actor.update_from_flat()
+        out = env.rollout_host(host, T, -K, actor=actor, ep_return_host=ret_host, replay=(bs, bo), stats=stats)
+        return float(out["stats"].cpu()[0])                       # D2H of the step's metric (sum of episode returns)
+
+    e2e_steps = max(2, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * T * e2e_steps / float(e2e_t.item())
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (plant, prior, obs; actor: f16 tensor-core operands, f32 accumulate)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "T": T, "actor": f"ResidualIntegratorModularPPO-{H}",
+                       "env": "NonLinearWaterTankChangingParamUniformGoalIntegrator-SquareDistance-v2", "noise_scale": 0.01,
+                       "policy": "stochastic (explore_env)", "replay": "GPU-resident, time-major [T,n,S]+[T,n,4] fp32",
+                       "l2": f"each step streams {(bs.numel() + bo.numel()) * 4 / 1e9:.2f} GB of replay rows through L2 (>> 126 MB), "
+                             "which flushes it between timed steps",
+                       "sharding": "contiguous env-id ranges per rank, Philox keyed by global env id"},
+            "clocks": clocks, "gpu_launches": args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "WaterTankVec.rollout_host -> pime_wt_rollout_host_f32 (pinned host state in, ep_return + final state out)"},
+            "episode_stats": {"mean_return": st[0] / max(st[2], 1), "episodes": st[2]}}
+
+    if rank == 0:
+        flops = FLOPS_PER_STEP.get(("modular", H, S))
+        step_ms = float(np.mean(kernel_ms))
+        if flops:
+            ach = n * T * flops / (step_ms * 1e-3) / 1e12
+            line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
+                                "traffic": None, "kernel": f"rollout_kernel<WtGlue<float>, modular, {H}>",
+                                "peak_source": pk["src"] + ", sustained bf16 (kernel runs for >100 ms)",
+                                "note": "co-limited by the MUFU pipe (1025 tanh + 40 sqrt per env-step), see sfu"}
+            sm_mhz = clocks.get("sm_mhz") or pk["sm_max"]
+            mufu = n * T * (TANH_PER_STEP[("modular", H, S)] + 40 + 6) / (step_ms * 1e-3)
+            mufu_peak = 148 * 16 * sm_mhz * 1e6
+            line["sfu"] = {"achieved_gops": mufu / 1e9, "peak_gops": mufu_peak / 1e9, "frac": mufu / mufu_peak,
+                           "note": "MUFU ops/s vs 148 SM x 16/clk at the median SM clock under load"}
+        if not args.no_aux:
+            line["roofline_step"] = aux_step_rooflines(V, pk)
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(H, S, T, args.cpu_seconds, sd)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def aux_step_rooflines(V, pk):
+    """Stand-alone gym-API step kernels (state round-trips HBM every call): the HBM-bound rows of SURVEY 8d."""
+    import torch
+    out = {}
+    n = 1 << 25  # 32 Mi envs: 1.2 GB of fp32 state per plant, far larger than L2
+    for name in ("wt", "ph"):
+        if name == "wt":
+            env = V.WaterTankVec(n, dtype=torch.float32, obs_mode="integrator", noise_scale=0.0)
+            nbytes = WT_STEP_BYTES_F32
+        else:
+            env = V.PHVec(n, dtype=torch.float32)
+            nbytes = PH_STEP_BYTES_F32
+        env.reset()
+        act = torch.rand(n, device="cuda") * 2 - 1
+        import ctypes as C
+        import pime_b200._lib as L
+        reward = torch.empty(n, dtype=torch.float32, device="cuda")
+        done = torch.empty(n, dtype=torch.uint8, device="cuda")
+
+        def launch():
+            if name == "wt":
+                L.check(L.lib().pime_wt_step_f32(C.byref(env.cfg), C.c_int64(n), C.byref(env._st), L.ptr(act), None, None,
+                                                 C.c_uint64(0), C.c_uint64(0), C.c_uint32(0), None, L.ptr(reward), L.ptr(done),
+                                                 L.stream_ptr()))
+            else:
+                L.check(L.lib().pime_ph_step_f32(C.byref(env.cfg), L.ptr(env.table), C.c_int64(n), C.byref(env._st), L.ptr(act),
+                                                 None, L.ptr(reward), L.ptr(done), L.ptr(env.status), L.stream_ptr()))
+        for _ in range(3):
+            launch()
+        torch.cuda.synchronize()
+        reps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            launch()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = n * nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+                     "env_steps_per_s": n / (ms * 1e-3), "bytes_per_env_step": nbytes, "envs": n,
+                     "kernel": f"{name}_step_kernel<float>", "peak_source": pk["src"]}
+        del env
+        torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,207 @@
+// plants.cuh -- per-env device arithmetic of the two gym_control plants (one thread = one env, state in registers).
+// Used by the stand-alone step/reset kernels (step.cu) and by the fused rollout kernels (rollout_impl.cuh).
+#pragma once
+
+#include "pime_common.cuh"
+
+namespace pime {
+
+// ============================================================================================== water tank
+template <typename T> struct WtConst {
+    T twoG, A1, A2, dt, Pmax, z1, thr, Imax, Ipunish, noise_scale;
+    // f32 fast path: sqrt(2G)*dt/A folded once per launch
+    T sq2G_dt_over_A1, sq2G_dt_over_A2, dt_over_A1;
+    T a1_lo, a1_w, a2_lo, a2_w, Kp_lo, Kp_w, h_lo, h_w, r_lo, r_w;
+    int n_discrete, max_step, reward_type, obs_mode, num_stack;
+};
+
+template <typename T> inline WtConst<T> make_wt_const(const pime_wt_config &c) {
+    WtConst<T> k;
+    k.twoG = (T)(2 * c.G);
+    k.A1 = (T)c.A1; k.A2 = (T)c.A2;
+    k.dt = (T)(c.sample_t / (double)c.n_discrete);  // delta_t (nonlinear_watertank.py:151)
+    k.Pmax = (T)c.P_max_action;
+    k.z1 = (T)c.z1; k.thr = (T)c.distance_threshold; k.Imax = (T)c.integral_max; k.Ipunish = (T)c.integral_punish;
+    k.noise_scale = (T)c.noise_scale;
+    double dt = c.sample_t / (double)c.n_discrete;
+    k.sq2G_dt_over_A1 = (T)(sqrt(2 * c.G) * dt / c.A1);
+    k.sq2G_dt_over_A2 = (T)(sqrt(2 * c.G) * dt / c.A2);
+    k.dt_over_A1 = (T)(dt / c.A1);
+    k.a1_lo = (T)c.a1_lo; k.a1_w = (T)(c.a1_hi - c.a1_lo);
+    k.a2_lo = (T)c.a2_lo; k.a2_w = (T)(c.a2_hi - c.a2_lo);
+    k.Kp_lo = (T)c.Kp_lo; k.Kp_w = (T)(c.Kp_hi - c.Kp_lo);
+    k.h_lo = (T)c.h_lo; k.h_w = (T)(c.h_hi - c.h_lo);
+    k.r_lo = (T)c.r_lo; k.r_w = (T)(c.r_hi - c.r_lo);
+    k.n_discrete = c.n_discrete; k.max_step = c.max_step; k.reward_type = c.reward_type;
+    k.obs_mode = c.obs_mode; k.num_stack = c.num_stack;
+    return k;
+}
+
+template <typename T> struct WtEnv {
+    T h1, h2, r, I, a1, a2, Kp;
+    int t;
+};
+
+// 20 Euler sub-steps (nonlinear_watertank.py:805-809).  f64: the reference's operation order, no contraction.
+__device__ __forceinline__ void wt_integrate(const WtConst<double> &c, double a1, double a2, double Kp, double u, double &x1,
+                                             double &x2) {
+    using N = Num<double>;
+    const double na1 = N::div(-a1, c.A1), pa1 = N::div(a1, c.A2), pa2 = N::div(a2, c.A2);
+    const double kpu = N::mul(N::div(Kp, c.A1), u);
+    for (int k = 0; k < c.n_discrete; ++k) {
+        double s1 = N::sqrt(N::mul(c.twoG, x1));
+        double s2 = N::sqrt(N::mul(c.twoG, x2));
+        double n1 = N::add(x1, N::mul(N::add(N::mul(na1, s1), kpu), c.dt));
+        double n2 = N::add(x2, N::mul(N::sub(N::mul(pa1, s1), N::mul(pa2, s2)), c.dt));
+        x1 = clip_lo0(n1);
+        x2 = clip_lo0(n2);
+    }
+}
+
+// f32: same recurrence with the constants folded (sqrt(2G h) = sqrt(2G) sqrt(h)) -> 2 MUFU + 4 FMA + 2 FMNMX per sub-step.
+__device__ __forceinline__ void wt_integrate(const WtConst<float> &c, float a1, float a2, float Kp, float u, float &x1, float &x2) {
+    const float k1 = -a1 * c.sq2G_dt_over_A1;  // coefficient of sqrt(h1) in h1'
+    const float k2a = a1 * c.sq2G_dt_over_A2;  // coefficient of sqrt(h1) in h2'
+    const float k2b = -a2 * c.sq2G_dt_over_A2; // coefficient of sqrt(h2) in h2'
+    const float b1 = Kp * u * c.dt_over_A1;    // pump inflow per sub-step
+#pragma unroll 4
+    for (int k = 0; k < c.n_discrete; ++k) {
+        float s1 = Num<float>::sqrt(x1);
+        float s2 = Num<float>::sqrt(x2);
+        float n1 = fmaf(k1, s1, x1 + b1);
+        float n2 = fmaf(k2a, s1, fmaf(k2b, s2, x2));
+        x1 = fmaxf(n1, 0.0f);
+        x2 = fmaxf(n2, 0.0f);
+    }
+}
+
+// One env.step(): NonLinearWaterTankUniformGoalIntegrator.step (:800-826) / base step (:274-297).
+template <typename T>
+__device__ __forceinline__ void wt_advance(const WtConst<T> &c, WtEnv<T> &e, T action, T nz1, T nz2, T &reward, bool &done) {
+    using N = Num<T>;
+    e.t += 1;                                                                                   // :801
+    T u = N::add(N::div(N::mul(action, c.Pmax), (T)2), N::div(c.Pmax, (T)2));                   // :260 (no clip)
+    T x1 = e.h1, x2 = e.h2;
+    wt_integrate(c, e.a1, e.a2, e.Kp, u, x1, x2);
+    x1 = clip_lo0(N::add(x1, nz1));                                                             // :810-813
+    x2 = clip_lo0(N::add(x2, nz2));
+    T rew = reward_of<T>(c.reward_type, N::abs(N::sub(x2, e.r)), c.z1, c.thr);                  // :815
+    done = e.t >= c.max_step;                                                                   // :816-821
+    if (c.obs_mode == PIME_WT_OBS_INTEGRATOR) {
+        T integ = N::add(e.I, N::sub(e.r, x2));                                                 // :822-823
+        rew = N::add(rew, N::mul(-c.Ipunish, N::abs(integ)));                                   // :824
+        e.I = clampT(integ, -c.Imax, c.Imax);                                                   // :825
+    }
+    e.h1 = x1;
+    e.h2 = x2;
+    reward = rew;
+}
+
+// reset_all()/reset_r() (:902-939): u[] are the six uniforms of reset_uniforms().
+template <typename T> __device__ __forceinline__ void wt_reset(const WtConst<T> &c, WtEnv<T> &e, const double u[6], bool resample) {
+    if (resample) {  // sample_parameters (:890-894): low + (high-low)*u
+        e.a1 = (T)((double)c.a1_lo + (double)c.a1_w * u[0]);
+        e.a2 = (T)((double)c.a2_lo + (double)c.a2_w * u[1]);
+        e.Kp = (T)((double)c.Kp_lo + (double)c.Kp_w * u[2]);
+    }
+    e.h1 = (T)((double)c.h_lo + (double)c.h_w * u[3]);  // :912
+    e.h2 = (T)((double)c.h_lo + (double)c.h_w * u[4]);
+    e.r = (T)((double)c.r_lo + (double)c.r_w * u[5]);   // :913
+    e.t = 0;
+    e.I = (T)0;
+}
+
+// ============================================================================================== pH
+template <typename T> struct PhConst {
+    T act_low, act_w, thr, Imax, Ipunish, act_punish, sample_t;
+    T qww_lo, qww_w, qc_lo, qc_w, x_lo, x_w, r_lo, r_w;
+    int reward_type, integrator_mode, max_episode_steps, table_len;
+};
+
+template <typename T> inline PhConst<T> make_ph_const(const pime_ph_config &c) {
+    PhConst<T> k;
+    k.act_low = (T)c.act_low; k.act_w = (T)(c.act_high - c.act_low);
+    k.thr = (T)c.distance_threshold; k.Imax = (T)c.integral_max; k.Ipunish = (T)c.integral_punish;
+    k.act_punish = (T)c.action_punishment; k.sample_t = (T)c.sample_t;
+    k.qww_lo = (T)c.qww_lo; k.qww_w = (T)(c.qww_hi - c.qww_lo);
+    k.qc_lo = (T)c.qc_lo; k.qc_w = (T)(c.qc_hi - c.qc_lo);
+    k.x_lo = (T)c.x_lo; k.x_w = (T)(c.x_hi - c.x_lo);
+    k.r_lo = (T)c.r_lo; k.r_w = (T)(c.r_hi - c.r_lo);
+    k.reward_type = c.reward_type; k.integrator_mode = c.integrator_mode;
+    k.max_episode_steps = c.max_episode_steps; k.table_len = c.table_len;
+    return k;
+}
+
+template <typename T> struct PhEnv {
+    T x, y, r, I, A, B, C;
+    int t;
+};
+
+// observe_state (ph.py:187-189): first i with MHCl[i] >= around(C*x,5)  ==  rint(C*x*1e5)  (MHCl[i] = i*1e-5;
+// equivalence checked on the reference in tests/golden/ph.npz).  Returns false when past the table (IndexError).
+__device__ __forceinline__ bool ph_lookup(const double *__restrict__ table, int table_len, double C, double x, double &y) {
+    double k = rint(__dmul_rn(__dmul_rn(C, x), 1e5));
+    long long i = (long long)k;
+    if (i < 0) i = 0;
+    if (i >= table_len) { y = table[table_len - 1]; return false; }
+    y = __ldg(table + i);
+    return true;
+}
+__device__ __forceinline__ bool ph_lookup(const float *__restrict__ table, int table_len, float C, float x, float &y) {
+    int i = __float2int_rn(C * x * 1e5f);
+    if (i < 0) i = 0;
+    if (i >= table_len) { y = table[table_len - 1]; return false; }
+    y = __ldg(table + i);
+    return true;
+}
+
+// PH1DUniformGoalIntegrator.step (ph.py:320-348) / _NoBound.step (:449-478) + TimeLimit.
+template <typename T>
+__device__ __forceinline__ bool ph_advance(const PhConst<T> &c, const T *__restrict__ table, PhEnv<T> &e, T action, T &reward,
+                                           bool &done) {
+    using N = Num<T>;
+    T a = clampT(action, (T)-1, (T)1);                                                          // :321
+    e.t += 1;                                                                                   // :325
+    T u = N::add(c.act_low, N::mul(c.act_w, N::div(N::sub(a, (T)-1), (T)2)));                   // :155-159
+    T xn = N::add(N::mul(e.A, e.x), N::mul(e.B, u));                                            // :330
+    T y;
+    bool ok = ph_lookup(table, c.table_len, e.C, xn, y);                                        // :188
+    T rew = reward_of<T>(c.reward_type, N::abs(N::sub(y, e.r)), (T)1, c.thr);                   // :334
+    rew = N::sub(rew, N::mul(c.act_punish, N::abs(u)));                                         // :336
+    if (c.integrator_mode != PIME_PH_NO_INTEGRATOR) {
+        T integ = N::add(e.I, N::sub(e.r, y));                                                  // :339-340
+        rew = N::add(rew, N::mul(-c.Ipunish, N::abs(integ)));                                   // :343
+        e.I = c.integrator_mode == PIME_PH_INTEGRATOR ? clampT(integ, -c.Imax, c.Imax) : integ; // :341 / :470
+    }
+    e.x = xn;
+    e.y = y;
+    reward = rew;
+    done = e.t >= c.max_episode_steps;  // gym TimeLimit (gym_control/__init__.py:6)
+    return ok;
+}
+
+// update_system (ph.py:114-121): closed form of the ZOH discretisation of qc_V/(s+qww_V).
+template <typename T> __device__ __forceinline__ void ph_update_system(T sample_t, T qww, T qc, T &A, T &B, T &C) {
+    double a = exp(-(double)qww * (double)sample_t);
+    A = (T)a;
+    B = (T)((1.0 - a) / (double)qww);
+    C = qc;
+}
+
+template <typename T>
+__device__ __forceinline__ bool ph_reset(const PhConst<T> &c, const T *__restrict__ table, PhEnv<T> &e, T &qww, T &qc,
+                                         const double u[6], bool resample) {
+    if (resample) {  // sample_parameters (:409-410) + update_system (:414)
+        qww = (T)((double)c.qww_lo + (double)c.qww_w * u[0]);
+        qc = (T)((double)c.qc_lo + (double)c.qc_w * u[1]);
+        ph_update_system<T>(c.sample_t, qww, qc, e.A, e.B, e.C);
+    }
+    e.x = (T)((double)c.x_lo + (double)c.x_w * u[2]);   // :420
+    bool ok = ph_lookup(table, c.table_len, e.C, e.x, e.y); // :422
+    e.t = 0;
+    e.r = (T)((double)c.r_lo + (double)c.r_w * u[3]);   // :424
+    e.I = (T)0;
+    return ok;
+}
+
+}  // namespace pime

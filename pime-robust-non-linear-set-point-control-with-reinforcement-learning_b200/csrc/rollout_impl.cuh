@@ -1,0 +1,320 @@
+// rollout_impl.cuh -- the fused kernel: T steps of plant + prior + float32 observation + residual actor for 128 envs
+// per CTA, state in registers for the whole launch.  Replaces the per-step Python loop of
+// AgentResidualPPO.explore_env (elegantrl/agent_residual.py:52-69) and get_episode_return (elegantrl/run.py:600-619).
+#pragma once
+
+#include "plants.cuh"
+#include "tc_mlp.cuh"
+
+namespace pime {
+
+constexpr int kMaxS = 32;
+
+struct RolloutParams {
+    int64_t n;
+    int T, deterministic, auto_reset, has_actor;
+    float a_std;            // exp(a_std_log)
+    double reward_scale, gamma;
+    uint64_t seed, env_offset;
+    uint32_t tick0;
+    int S;
+    double priorK[kMaxS];
+    const float *eps;
+    const void *pn1, *pn2;
+    float *buf_state, *buf_other;
+    void *env_action;
+    double *stats;
+    int32_t *status;
+};
+
+// ------------------------------------------------------------------------------------------------ plant glue
+template <typename T> struct WtGlue {
+    using Real = T;
+    WtConst<T> c;
+    T *h1, *h2, *r, *I, *a1, *a2, *Kp, *ep_return, *frames;
+    int32_t *t;
+    uint32_t *episode;
+
+    struct Env {
+        WtEnv<T> e;
+        T ret;
+        uint32_t episode;
+        T fr[30];  // stacking only (local memory); obs history, oldest first
+    };
+
+    __device__ __forceinline__ int obs_dim() const {
+        return c.obs_mode == PIME_WT_OBS_GOAL ? 3 : (c.obs_mode == PIME_WT_OBS_INTEGRATOR ? 4 : 3 * c.num_stack);
+    }
+    __device__ __forceinline__ void load(Env &v, int64_t i, int64_t n) const {
+        v.e.h1 = h1[i]; v.e.h2 = h2[i]; v.e.r = r[i];
+        v.e.I = c.obs_mode == PIME_WT_OBS_INTEGRATOR ? I[i] : (T)0;
+        v.e.a1 = a1[i]; v.e.a2 = a2[i]; v.e.Kp = Kp[i];
+        v.e.t = t[i];
+        v.ret = ep_return ? ep_return[i] : (T)0;
+        v.episode = episode[i];
+        if (c.obs_mode == PIME_WT_OBS_STACKING)
+            for (int j = 0; j < 3 * c.num_stack; ++j) v.fr[j] = frames[(int64_t)j * n + i];
+    }
+    __device__ __forceinline__ void store(const Env &v, int64_t i, int64_t n) const {
+        h1[i] = v.e.h1; h2[i] = v.e.h2; r[i] = v.e.r;
+        if (c.obs_mode == PIME_WT_OBS_INTEGRATOR) I[i] = v.e.I;
+        a1[i] = v.e.a1; a2[i] = v.e.a2; Kp[i] = v.e.Kp;
+        t[i] = v.e.t;
+        if (ep_return) ep_return[i] = v.ret;
+        episode[i] = v.episode;
+        if (c.obs_mode == PIME_WT_OBS_STACKING)
+            for (int j = 0; j < 3 * c.num_stack; ++j) frames[(int64_t)j * n + i] = v.fr[j];
+    }
+    // float32(obs): elegantrl/env.py:46,72
+    __device__ __forceinline__ void observe(const Env &v, float *obs) const {
+        if (c.obs_mode == PIME_WT_OBS_STACKING) {
+            for (int j = 0; j < 3 * c.num_stack; ++j) obs[j] = (float)v.fr[j];
+        } else {
+            obs[0] = (float)v.e.h1; obs[1] = (float)v.e.h2; obs[2] = (float)v.e.r;
+            if (c.obs_mode == PIME_WT_OBS_INTEGRATOR) obs[3] = (float)v.e.I;
+        }
+    }
+    __device__ __forceinline__ bool uses_process_noise() const { return c.noise_scale > (T)0; }
+    __device__ __forceinline__ T noise_sigma() const { return c.noise_scale; }
+    __device__ __forceinline__ bool advance(Env &v, T action, T nz1, T nz2, T &rew, bool &done) const {
+        wt_advance(c, v.e, action, nz1, nz2, rew, done);
+        if (c.obs_mode == PIME_WT_OBS_STACKING) {  // frames.append(state) (nonlinear_watertank.py:1145-1146)
+            const int m = 3 * c.num_stack;
+            for (int j = 0; j < m - 3; ++j) v.fr[j] = v.fr[j + 3];
+            v.fr[m - 3] = v.e.h1; v.fr[m - 2] = v.e.h2; v.fr[m - 1] = v.e.r;
+        }
+        return true;
+    }
+    __device__ __forceinline__ T tracking_error(const Env &v) const { return Num<T>::abs(v.e.r - v.e.h2); }
+    __device__ __forceinline__ bool reset(Env &v, uint64_t seed, uint64_t index) const {
+        double u[6];
+        reset_uniforms(seed, index, v.episode, u);
+        wt_reset(c, v.e, u, true);
+        v.episode += 1;
+        if (c.obs_mode == PIME_WT_OBS_STACKING)
+            for (int j = 0; j < c.num_stack; ++j) { v.fr[3 * j] = v.e.h1; v.fr[3 * j + 1] = v.e.h2; v.fr[3 * j + 2] = v.e.r; }
+        return true;
+    }
+};
+
+template <typename T> struct PhGlue {
+    using Real = T;
+    PhConst<T> c;
+    const T *table;
+    T *x, *y, *r, *I, *A, *B, *C, *qww, *qc, *ep_return;
+    int32_t *t;
+    uint32_t *episode;
+
+    struct Env {
+        PhEnv<T> e;
+        T qww, qc, ret;
+        uint32_t episode;
+    };
+    __device__ __forceinline__ int obs_dim() const { return c.integrator_mode == PIME_PH_NO_INTEGRATOR ? 2 : 3; }
+    __device__ __forceinline__ void load(Env &v, int64_t i, int64_t) const {
+        v.e.x = x[i]; v.e.y = y[i]; v.e.r = r[i];
+        v.e.I = c.integrator_mode != PIME_PH_NO_INTEGRATOR ? I[i] : (T)0;
+        v.e.A = A[i]; v.e.B = B[i]; v.e.C = C[i];
+        v.e.t = t[i];
+        v.qww = qww[i]; v.qc = qc[i];
+        v.ret = ep_return ? ep_return[i] : (T)0;
+        v.episode = episode[i];
+    }
+    __device__ __forceinline__ void store(const Env &v, int64_t i, int64_t) const {
+        x[i] = v.e.x; y[i] = v.e.y; r[i] = v.e.r;
+        if (c.integrator_mode != PIME_PH_NO_INTEGRATOR) I[i] = v.e.I;
+        A[i] = v.e.A; B[i] = v.e.B; C[i] = v.e.C;
+        t[i] = v.e.t;
+        qww[i] = v.qww; qc[i] = v.qc;
+        if (ep_return) ep_return[i] = v.ret;
+        episode[i] = v.episode;
+    }
+    __device__ __forceinline__ void observe(const Env &v, float *obs) const {
+        obs[0] = (float)v.e.y; obs[1] = (float)v.e.r;
+        if (c.integrator_mode != PIME_PH_NO_INTEGRATOR) obs[2] = (float)v.e.I;
+    }
+    __device__ __forceinline__ bool uses_process_noise() const { return false; }
+    __device__ __forceinline__ T noise_sigma() const { return (T)0; }
+    __device__ __forceinline__ bool advance(Env &v, T action, T, T, T &rew, bool &done) const {
+        return ph_advance(c, table, v.e, action, rew, done);
+    }
+    __device__ __forceinline__ T tracking_error(const Env &v) const { return Num<T>::abs(v.e.r - v.e.y); }
+    __device__ __forceinline__ bool reset(Env &v, uint64_t seed, uint64_t index) const {
+        double u[6];
+        reset_uniforms(seed, index, v.episode, u);
+        bool ok = ph_reset(c, table, v.e, v.qww, v.qc, u, true);
+        v.episode += 1;
+        return ok;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ the kernel
+template <typename Plant, int KIND, int H, int MINB>
+__global__ void __launch_bounds__(tc::kThreads, MINB) rollout_kernel(Plant plant, tc::MlpParams mp, RolloutParams rp) {
+    using T = typename Plant::Real;
+    using N = Num<T>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    tc::Engine<KIND, H> eng;
+    if (rp.has_actor) eng.setup(smem, mp);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    double s_ret = 0.0, s_ret2 = 0.0, s_cnt = 0.0, s_err = 0.0, s_rew = 0.0, s_steps = 0.0;
+    bool fault = false;
+
+    if (warp < 4) {
+        const int64_t n = rp.n;
+        const int64_t i = (int64_t)blockIdx.x * tc::kRows + tid;
+        const bool live = i < n;
+        const int64_t ii = live ? i : n - 1;  // tail rows shadow the last env and write nothing
+        typename Plant::Env env;
+        plant.load(env, ii, n);
+        const int S = rp.S;
+        float obs[kMaxS];
+        for (int s = 0; s < rp.T; ++s) {
+            plant.observe(env, obs);
+            const float a_avg = rp.has_actor ? eng.forward(tid, obs) : 0.0f;
+            // ---- noise
+            float eps = 0.0f, z0 = 0.0f, z1 = 0.0f;
+            const int64_t q = (int64_t)s * n + ii;
+            const bool need_eps = !rp.deterministic && rp.eps == nullptr;
+            const bool need_pn = plant.uses_process_noise() && rp.pn1 == nullptr;
+            if (need_eps || need_pn) {
+                const Philox4 w = philox4x32_10(rp.seed, rp.env_offset + (uint64_t)ii, rp.tick0 + (uint32_t)s, kStreamStep);
+                if (need_pn) box_muller(w.v[0], w.v[1], z0, z1);
+                if (need_eps) { float e1; box_muller(w.v[2], w.v[3], eps, e1); }
+            }
+            if (!rp.deterministic && rp.eps) eps = rp.eps[q];
+            T nz1 = (T)0, nz2 = (T)0;
+            if (plant.uses_process_noise()) {
+                if (rp.pn1) { nz1 = ((const T *)rp.pn1)[q]; nz2 = ((const T *)rp.pn2)[q]; }
+                else { nz1 = (T)z0 * plant.noise_sigma(); nz2 = (T)z1 * plant.noise_sigma(); }
+            } else if (rp.pn1) { nz1 = ((const T *)rp.pn1)[q]; nz2 = ((const T *)rp.pn2)[q]; }
+            // ---- action = tanh(a_raw) + obs32 . priorK   (agent_residual.py:61 / net_residual.py:167-170)
+            float a_raw;
+            T action;
+            if (rp.deterministic) {
+                float prior = 0.0f;
+                for (int k = 0; k < S; ++k) prior = fmaf(obs[k], (float)rp.priorK[k], prior);
+                a_raw = a_avg;
+                action = (T)(tanhf(a_avg) + prior);
+            } else {
+                T prior = (T)0;
+                for (int k = 0; k < S; ++k) prior = N::add(prior, N::mul((T)obs[k], (T)rp.priorK[k]));
+                a_raw = a_avg + eps * rp.a_std;   // net_residual.py:176-180
+                action = N::add((T)tanhf(a_raw), prior);
+            }
+            // ---- plant step
+            T rew;
+            bool done;
+            if (!plant.advance(env, action, nz1, nz2, rew, done)) fault = true;
+            env.ret += rew;
+            if (live) {
+                if (rp.buf_state) {  // replay row (agent_residual.py:64-65; replay.py:278-291), time-major
+                    float *bs = rp.buf_state + q * S;
+                    if (S == 4) *reinterpret_cast<float4 *>(bs) = make_float4(obs[0], obs[1], obs[2], obs[3]);
+                    else for (int k = 0; k < S; ++k) bs[k] = obs[k];
+                    *reinterpret_cast<float4 *>(rp.buf_other + q * 4) =
+                        make_float4((float)((double)rew * rp.reward_scale), done ? 0.0f : (float)rp.gamma, a_raw, eps);
+                }
+                if (rp.env_action) ((T *)rp.env_action)[q] = action;
+                s_rew += (double)rew;
+                s_steps += 1.0;
+                if (done) {
+                    s_ret += (double)env.ret;
+                    s_ret2 += (double)env.ret * (double)env.ret;
+                    s_cnt += 1.0;
+                    s_err += (double)plant.tracking_error(env);
+                }
+            }
+            if (done && rp.auto_reset) {  // env.reset() -> reset_all(): new ensemble member (T4 in SURVEY.md)
+                if (!plant.reset(env, rp.seed, rp.env_offset + (uint64_t)ii)) fault = true;
+                env.ret = (T)0;
+            }
+        }
+        if (live) plant.store(env, i, n);
+    } else if (rp.has_actor && (tid & 31) == 0) {
+        if (warp == 4) eng.mma_loop(rp.T);
+        else eng.producer_loop(rp.T);
+    }
+
+    if (rp.has_actor) eng.teardown();
+
+    // ---- warp-shuffle reduction of the episode / set-point statistics, one atomic set per CTA
+    if (rp.stats) {
+        __shared__ double red[6][4];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s_ret += __shfl_xor_sync(0xffffffffu, s_ret, o);
+            s_ret2 += __shfl_xor_sync(0xffffffffu, s_ret2, o);
+            s_cnt += __shfl_xor_sync(0xffffffffu, s_cnt, o);
+            s_err += __shfl_xor_sync(0xffffffffu, s_err, o);
+            s_rew += __shfl_xor_sync(0xffffffffu, s_rew, o);
+            s_steps += __shfl_xor_sync(0xffffffffu, s_steps, o);
+        }
+        if (warp < 4 && (tid & 31) == 0) {
+            red[0][warp] = s_ret; red[1][warp] = s_ret2; red[2][warp] = s_cnt;
+            red[3][warp] = s_err; red[4][warp] = s_rew; red[5][warp] = s_steps;
+        }
+        __syncthreads();
+        if (tid < 6) atomicAdd(rp.stats + tid, red[tid][0] + red[tid][1] + red[tid][2] + red[tid][3]);
+    }
+    if (fault && rp.status) atomicMin(rp.status, (int32_t)PIME_ERANGE);
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+template <typename Plant, int KIND, int H>
+int launch_rollout_kh(const Plant &plant, const tc::PackLayout *L, const void *pack, const RolloutParams &rp, cudaStream_t stream) {
+    using G = tc::Geo<KIND, H>;
+    constexpr int MINB = G::SmemBytes <= 113 * 1024 ? 2 : 1;
+    auto kern = rollout_kernel<Plant, KIND, H, MINB>;
+    const int smem = rp.has_actor ? G::SmemBytes : 0;
+    PIME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SmemBytes));
+    tc::MlpParams mp = rp.has_actor ? tc::make_mlp_params(*L, pack) : tc::MlpParams{};
+    const int64_t grid = (rp.n + tc::kRows - 1) / tc::kRows;
+    PIME_REQUIRE(grid <= 0x7fffffffLL, "too many envs for one launch");
+    kern<<<(unsigned)grid, tc::kThreads, smem, stream>>>(plant, mp, rp);
+    PIME_LAUNCH_CHECK();
+    return PIME_OK;
+}
+
+template <typename Plant, int KIND>
+int launch_rollout_k(const Plant &plant, const tc::PackLayout *L, const void *pack, const RolloutParams &rp, int H,
+                     cudaStream_t stream) {
+    switch (H) {
+        case 32: return launch_rollout_kh<Plant, KIND, 32>(plant, L, pack, rp, stream);
+        case 64: return launch_rollout_kh<Plant, KIND, 64>(plant, L, pack, rp, stream);
+        case 128: return launch_rollout_kh<Plant, KIND, 128>(plant, L, pack, rp, stream);
+        case 256: return launch_rollout_kh<Plant, KIND, 256>(plant, L, pack, rp, stream);
+    }
+    set_error("mid_dim must be 32, 64, 128 or 256");
+    return PIME_EINVAL;
+}
+
+// Fills RolloutParams from the public argument block; returns the pack layout in L when an actor is given.
+inline int fill_rollout_params(const pime_rollout_args *a, int64_t n, int S, RolloutParams &rp, tc::PackLayout &L) {
+    PIME_REQUIRE(a, "null rollout args");
+    PIME_REQUIRE(a->T >= 1, "T must be >= 1");
+    PIME_REQUIRE(a->priorK_host, "priorK_host is required (pass zeros for no prior)");
+    PIME_REQUIRE(S >= 1 && S <= kMaxS, "observation dim");
+    PIME_REQUIRE((a->buf_state == nullptr) == (a->buf_other == nullptr), "buf_state/buf_other must both be given or both NULL");
+    PIME_REQUIRE((a->pnoise1 == nullptr) == (a->pnoise2 == nullptr), "pnoise1/pnoise2 must both be given or both NULL");
+    rp = RolloutParams{};
+    rp.n = n; rp.T = a->T; rp.deterministic = a->deterministic; rp.auto_reset = a->auto_reset;
+    rp.has_actor = a->actor != nullptr;
+    rp.a_std = expf(a->a_std_log);
+    rp.reward_scale = a->reward_scale; rp.gamma = a->gamma; rp.seed = a->seed; rp.env_offset = a->env_offset; rp.tick0 = a->tick0;
+    rp.S = S;
+    for (int k = 0; k < kMaxS; ++k) rp.priorK[k] = k < S ? a->priorK_host[k] : 0.0;
+    rp.eps = a->eps; rp.pn1 = a->pnoise1; rp.pn2 = a->pnoise2;
+    rp.buf_state = a->buf_state; rp.buf_other = a->buf_other; rp.env_action = a->env_action;
+    rp.stats = a->stats; rp.status = a->status;
+    if (rp.has_actor) {
+        PIME_REQUIRE(a->actor_pack, "actor_pack is NULL");
+        PIME_REQUIRE(a->actor->kind == PIME_ACTOR_PLAIN || a->actor->kind == PIME_ACTOR_MODULAR, "actor kind");
+        PIME_REQUIRE(a->actor->state_dim == S, "actor state_dim does not match the env observation");
+        PIME_REQUIRE(tc::make_pack_layout(*a->actor, L), "unsupported actor dimensions");
+    }
+    return PIME_OK;
+}
+
+}  // namespace pime

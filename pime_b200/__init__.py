@@ -1,0 +1,10 @@
+"""Import alias for the package directory ``pime-robust-non-linear-set-point-control-with-reinforcement-learning_b200``
+(whose name is not a valid Python identifier)."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))),
+                      "pime-robust-non-linear-set-point-control-with-reinforcement-learning_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+del _os, _f, _real
