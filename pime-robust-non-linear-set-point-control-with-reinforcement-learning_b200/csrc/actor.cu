@@ -3,67 +3,40 @@
 
 namespace pime {
 
-struct PackKernelArgs {
-    tc::PackLayout L;
-};
-
-// fp32 torch-layout parameters -> kernel image (fp32 vectors + fp16 weight blocks in tcgen05 operand layout)
-__global__ void __launch_bounds__(256) pack_kernel(PackKernelArgs a, const float *__restrict__ p, uint8_t *__restrict__ out) {
-    const tc::PackLayout &L = a.L;
-    const int H = L.H, Hh = H / 2, S = L.S;
-    float *f32 = reinterpret_cast<float *>(out);
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    // ---- fp32 section
-    for (int64_t j = tid0; j < L.f32_floats; j += stride) {
+// fp32 torch-layout parameters -> kernel image: the block program (header) + fp16 weight blocks in tcgen05 operand
+// layout ([K/8 core-matrix columns][N rows][8 fp16]).  One CTA per block.
+__global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ tc::PackLayout L, const float *__restrict__ p,
+                                                   uint8_t *__restrict__ out) {
+    const int b = blockIdx.x;
+    const tc::Blk B = L.blk[b];
+    const tc::BlkSrc s = L.bsrc[b];
+    if (threadIdx.x == 0) reinterpret_cast<tc::Blk *>(out)[b] = B;
+    const int NB = B.nb8 * 8, K = B.k16s * 16;
+    __half *dst = reinterpret_cast<__half *>(out + tc::kHeaderBytes + B.src_off);
+    for (int e = threadIdx.x; e < NB * K; e += blockDim.x) {
+        const int n = e / K, k = e % K;
         float v = 0.0f;
-        const int jj = (int)j;
-        if (L.kind == PIME_ACTOR_MODULAR) {
-            const int So = S - L.D;
-            if (jj < 4 * H) {            // l1o: (w0,w1,w2,b) per hidden unit
-                const int u = jj / 4, c = jj % 4;
-                v = c == 3 ? p[L.src[1] + u] : (c < So ? p[L.src[0] + u * So + c] : 0.0f);
-            } else if (jj < 6 * H) {     // l1i: (w,b)
-                const int u = (jj - 4 * H) / 2, c = (jj - 4 * H) % 2;
-                v = c == 0 ? p[L.src[4] + u] : p[L.src[5] + u];
-            } else if (jj < 7 * H) {     // b1 = cat(bo1, bi1)
-                const int c = jj - 6 * H;
-                v = c < Hh ? p[L.src[3] + c] : p[L.src[7] + c - Hh];
-            } else if (jj < 9 * H) {     // ep2: (bn0[c], Wn1[c])
-                const int c = (jj - 7 * H) / 2, w = (jj - 7 * H) % 2;
-                v = w == 0 ? p[L.src[9] + c] : p[L.src[10] + c];
-            } else if (jj == 9 * H) {
-                v = p[L.src[11]];
+        bool lo = false;
+        if (n < s.n_real) {
+            const int u = s.n0 + n;
+            if (s.type == tc::SRC_HID) {
+                v = p[s.w_off + (int64_t)u * s.ld + s.k0 + k];
+            } else if (s.type == tc::SRC_BIAS) {
+                if (k < 2) { v = p[s.b_off + u]; lo = k == 1; }
+            } else {  // SRC_L1: [W_hi | W_hi | W_lo (3 terms) | b_hi b_lo] against [in_hi | in_lo | in_hi | 1 1]
+                const int kk = s.k0 + k, nw = L.nterms * L.nin;
+                if (kk < nw) {
+                    const int t = kk / L.nin, c = kk % L.nin;
+                    if (c >= s.c0 && c < s.c0 + s.cN) { v = p[s.w_off + (int64_t)u * s.ld + (c - s.c0)]; lo = t == 2; }
+                } else if (kk < nw + 2) {
+                    v = p[s.b_off + u];
+                    lo = kk == nw + 1;
+                }
             }
-        } else {
-            if (jj < H) v = p[L.src[1] + jj];
-            else if (jj < 2 * H) v = p[L.src[3] + jj - H];
-            else if (jj < 4 * H) {
-                const int c = (jj - 2 * H) / 2, w = (jj - 2 * H) % 2;
-                v = w == 0 ? p[L.src[5] + c] : p[L.src[6] + c];
-            } else if (jj == 4 * H) v = p[L.src[7]];
         }
-        f32[j] = v;
-    }
-    // ---- fp16 section
-    __half *f16 = reinterpret_cast<__half *>(out + L.f16_off);
-    for (int ph = 0; ph < 3; ++ph) {
-        const int N = L.phN[ph], K = L.phK[ph], NB = L.phNB[ph], nbn = N / NB;
-        const int64_t total = (int64_t)N * K;
-        for (int64_t e = tid0; e < total; e += stride) {
-            const int n = (int)(e / K), k = (int)(e % K);
-            float v;
-            if (L.kind != PIME_ACTOR_MODULAR && ph == 0) {  // [W0 | W0 | 0]: multiplies [obs_hi | obs_lo | 0]
-                v = k < S ? p[L.src_w[0] + n * S + k] : (k < 2 * S ? p[L.src_w[0] + n * S + (k - S)] : 0.0f);
-            } else {
-                v = p[L.src_w[ph] + (int64_t)n * L.src_ld[ph] + k];
-            }
-            const int nb = n / NB, nl = n % NB, kb = k / tc::KB, kl = k % tc::KB;
-            const int64_t blk = (int64_t)kb * nbn + nb;
-            const int64_t byte_off = (int64_t)L.phOff[ph] + blk * ((int64_t)NB * tc::KB * 2) + (int64_t)(kl / 8) * (NB * 16) +
-                                     (int64_t)nl * 16 + (kl % 8) * 2;
-            f16[byte_off / 2] = __float2half_rn(v);
-        }
+        __half h = __float2half_rn(v);
+        if (lo) h = __float2half_rn(v - __half2float(h));
+        dst[(size_t)(k / 8) * (NB * 8) + (size_t)n * 8 + (k % 8)] = h;
     }
 }
 
@@ -134,11 +107,11 @@ int64_t pime_actor_pack_bytes(const pime_actor_config *cfg) {
 
 int pime_actor_pack(const pime_actor_config *cfg, const float *params, void *pack, void *stream) {
     PIME_REQUIRE(cfg && params && pack, "null pointer");
-    PackKernelArgs a;
-    PIME_REQUIRE(tc::make_pack_layout(*cfg, a.L), "unsupported actor dimensions (H in {32,64,128,256}, S <= 32, modular: S-1 <= 3)");
+    tc::PackLayout L;
+    PIME_REQUIRE(tc::make_pack_layout(*cfg, L), "unsupported actor dimensions (H in {32,64,128,256}, S <= 32, modular: S-1 <= 3)");
     PIME_REQUIRE(((uintptr_t)pack & 127) == 0, "pack must be 128-byte aligned");
     if (int rc = require_device()) return rc;
-    pack_kernel<<<kNumSMs, 256, 0, (cudaStream_t)stream>>>(a, params, (uint8_t *)pack);
+    pack_kernel<<<L.nblk, 256, 0, (cudaStream_t)stream>>>(L, params, (uint8_t *)pack);
     PIME_LAUNCH_CHECK();
     return PIME_OK;
 }
