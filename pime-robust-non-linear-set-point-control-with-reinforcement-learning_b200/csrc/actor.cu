@@ -40,24 +40,36 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ tc::P
     }
 }
 
-template <int KIND, int H, int MINB>
-__global__ void __launch_bounds__(tc::kThreads, MINB) actor_forward_kernel(tc::MlpParams mp, int64_t n, const float *__restrict__ obs,
-                                                                           float *__restrict__ out) {
+// Stand-alone forward over n rows (1 pass per group): the owners load the row-major observations and store net(obs).
+template <int KIND, int H>
+__global__ void __launch_bounds__(tc::kThreads, 1) actor_forward_kernel(tc::MlpParams mp, int64_t n, const float *__restrict__ obs,
+                                                                        float *__restrict__ out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     tc::Engine<KIND, H> eng;
     eng.setup(smem, mp);
     const int tid = threadIdx.x, warp = tid >> 5;
-    if (warp < 4) {
-        const int64_t i = (int64_t)blockIdx.x * tc::kRows + tid;
-        const bool live = i < n;
-        const int64_t ii = live ? i : n - 1;
+    if (warp < 8) {
+        eng.worker_loop(2);
+    } else if (warp < 12) {
+        const int row = tid - tc::kWorkerThreads;
         float o[32];
-        for (int k = 0; k < mp.S; ++k) o[k] = obs[ii * mp.S + k];
-        const float a = eng.forward(tid, o);
-        if (live) out[i] = a;
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+            const int64_t i = (int64_t)blockIdx.x * tc::kTileEnvs + g * tc::kRows + row;
+            const int64_t ii = i < n ? i : n - 1;
+            for (int k = 0; k < mp.S; ++k) o[k] = obs[ii * mp.S + k];
+            eng.write_obs(row, g, o);
+        }
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+            const int64_t i = (int64_t)blockIdx.x * tc::kTileEnvs + g * tc::kRows + row;
+            const float a = eng.read_out(row, g);
+            if (i < n) out[i] = a;
+        }
+    } else if (warp == tc::kMmaWarp) {
+        eng.mma_loop(2);
     } else if ((tid & 31) == 0) {
-        if (warp == 4) eng.mma_loop(1);
-        else eng.producer_loop(1);
+        eng.producer_loop(2);
     }
     eng.teardown();
 }
@@ -65,10 +77,9 @@ __global__ void __launch_bounds__(tc::kThreads, MINB) actor_forward_kernel(tc::M
 template <int KIND, int H>
 static int launch_forward_kh(const tc::PackLayout &L, const void *pack, int64_t n, const float *obs, float *out, cudaStream_t stream) {
     using G = tc::Geo<KIND, H>;
-    constexpr int MINB = G::SmemBytes <= 113 * 1024 ? 2 : 1;
-    auto kern = actor_forward_kernel<KIND, H, MINB>;
+    auto kern = actor_forward_kernel<KIND, H>;
     PIME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SmemBytes));
-    const int64_t grid = (n + tc::kRows - 1) / tc::kRows;
+    const int64_t grid = (n + tc::kTileEnvs - 1) / tc::kTileEnvs;
     PIME_REQUIRE(grid <= 0x7fffffffLL, "too many rows for one launch");
     kern<<<(unsigned)grid, tc::kThreads, G::SmemBytes, stream>>>(tc::make_mlp_params(L, pack), n, obs, out);
     PIME_LAUNCH_CHECK();

@@ -148,100 +148,80 @@ template <typename T> struct PhGlue {
     }
 };
 
-// ------------------------------------------------------------------------------------------------ the kernel
-template <typename Plant, int KIND, int H, int MINB>
-__global__ void __launch_bounds__(tc::kThreads, MINB) rollout_kernel(Plant plant, tc::MlpParams mp, RolloutParams rp) {
+// ------------------------------------------------------------------------------------------------ one env step
+// Everything of one step that follows the actor forward, for the env owned by the calling thread:
+// noise, action = tanh(a_raw) + obs32 . priorK, plant step, replay row, statistics, auto-reset.
+template <typename Plant> struct Stepper {
     using T = typename Plant::Real;
     using N = Num<T>;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    tc::Engine<KIND, H> eng;
-    if (rp.has_actor) eng.setup(smem, mp);
-
-    const int tid = threadIdx.x, warp = tid >> 5;
     double s_ret = 0.0, s_ret2 = 0.0, s_cnt = 0.0, s_err = 0.0, s_rew = 0.0, s_steps = 0.0;
     bool fault = false;
 
-    if (warp < 4) {
+    __device__ __forceinline__ void step(const Plant &plant, const RolloutParams &rp, typename Plant::Env &env, const float *obs,
+                                         float a_avg, int s, int64_t ii, bool live) {
         const int64_t n = rp.n;
-        const int64_t i = (int64_t)blockIdx.x * tc::kRows + tid;
-        const bool live = i < n;
-        const int64_t ii = live ? i : n - 1;  // tail rows shadow the last env and write nothing
-        typename Plant::Env env;
-        plant.load(env, ii, n);
         const int S = rp.S;
-        float obs[kMaxS];
-        for (int s = 0; s < rp.T; ++s) {
-            plant.observe(env, obs);
-            const float a_avg = rp.has_actor ? eng.forward(tid, obs) : 0.0f;
-            // ---- noise
-            float eps = 0.0f, z0 = 0.0f, z1 = 0.0f;
-            const int64_t q = (int64_t)s * n + ii;
-            const bool need_eps = !rp.deterministic && rp.eps == nullptr;
-            const bool need_pn = plant.uses_process_noise() && rp.pn1 == nullptr;
-            if (need_eps || need_pn) {
-                const Philox4 w = philox4x32_10(rp.seed, rp.env_offset + (uint64_t)ii, rp.tick0 + (uint32_t)s, kStreamStep);
-                if (need_pn) box_muller(w.v[0], w.v[1], z0, z1);
-                if (need_eps) { float e1; box_muller(w.v[2], w.v[3], eps, e1); }
+        // ---- noise
+        float eps = 0.0f, z0 = 0.0f, z1 = 0.0f;
+        const int64_t q = (int64_t)s * n + ii;
+        const bool need_eps = !rp.deterministic && rp.eps == nullptr;
+        const bool need_pn = plant.uses_process_noise() && rp.pn1 == nullptr;
+        if (need_eps || need_pn) {
+            const Philox4 w = philox4x32_10(rp.seed, rp.env_offset + (uint64_t)ii, rp.tick0 + (uint32_t)s, kStreamStep);
+            if (need_pn) box_muller(w.v[0], w.v[1], z0, z1);
+            if (need_eps) { float e1; box_muller(w.v[2], w.v[3], eps, e1); }
+        }
+        if (!rp.deterministic && rp.eps) eps = rp.eps[q];
+        T nz1 = (T)0, nz2 = (T)0;
+        if (plant.uses_process_noise()) {
+            if (rp.pn1) { nz1 = ((const T *)rp.pn1)[q]; nz2 = ((const T *)rp.pn2)[q]; }
+            else { nz1 = (T)z0 * plant.noise_sigma(); nz2 = (T)z1 * plant.noise_sigma(); }
+        } else if (rp.pn1) { nz1 = ((const T *)rp.pn1)[q]; nz2 = ((const T *)rp.pn2)[q]; }
+        // ---- action = tanh(a_raw) + obs32 . priorK   (agent_residual.py:61 / net_residual.py:167-170)
+        float a_raw;
+        T action;
+        if (rp.deterministic) {
+            float prior = 0.0f;
+            for (int k = 0; k < S; ++k) prior = fmaf(obs[k], (float)rp.priorK[k], prior);
+            a_raw = a_avg;
+            action = (T)(tanhf(a_avg) + prior);
+        } else {
+            T prior = (T)0;
+            for (int k = 0; k < S; ++k) prior = N::add(prior, N::mul((T)obs[k], (T)rp.priorK[k]));
+            a_raw = a_avg + eps * rp.a_std;   // net_residual.py:176-180
+            action = N::add((T)tanhf(a_raw), prior);
+        }
+        // ---- plant step
+        T rew;
+        bool done;
+        if (!plant.advance(env, action, nz1, nz2, rew, done)) fault = true;
+        env.ret += rew;
+        if (live) {
+            if (rp.buf_state) {  // replay row (agent_residual.py:64-65; replay.py:278-291), time-major
+                float *bs = rp.buf_state + q * S;
+                if (S == 4) *reinterpret_cast<float4 *>(bs) = make_float4(obs[0], obs[1], obs[2], obs[3]);
+                else for (int k = 0; k < S; ++k) bs[k] = obs[k];
+                *reinterpret_cast<float4 *>(rp.buf_other + q * 4) =
+                    make_float4((float)((double)rew * rp.reward_scale), done ? 0.0f : (float)rp.gamma, a_raw, eps);
             }
-            if (!rp.deterministic && rp.eps) eps = rp.eps[q];
-            T nz1 = (T)0, nz2 = (T)0;
-            if (plant.uses_process_noise()) {
-                if (rp.pn1) { nz1 = ((const T *)rp.pn1)[q]; nz2 = ((const T *)rp.pn2)[q]; }
-                else { nz1 = (T)z0 * plant.noise_sigma(); nz2 = (T)z1 * plant.noise_sigma(); }
-            } else if (rp.pn1) { nz1 = ((const T *)rp.pn1)[q]; nz2 = ((const T *)rp.pn2)[q]; }
-            // ---- action = tanh(a_raw) + obs32 . priorK   (agent_residual.py:61 / net_residual.py:167-170)
-            float a_raw;
-            T action;
-            if (rp.deterministic) {
-                float prior = 0.0f;
-                for (int k = 0; k < S; ++k) prior = fmaf(obs[k], (float)rp.priorK[k], prior);
-                a_raw = a_avg;
-                action = (T)(tanhf(a_avg) + prior);
-            } else {
-                T prior = (T)0;
-                for (int k = 0; k < S; ++k) prior = N::add(prior, N::mul((T)obs[k], (T)rp.priorK[k]));
-                a_raw = a_avg + eps * rp.a_std;   // net_residual.py:176-180
-                action = N::add((T)tanhf(a_raw), prior);
-            }
-            // ---- plant step
-            T rew;
-            bool done;
-            if (!plant.advance(env, action, nz1, nz2, rew, done)) fault = true;
-            env.ret += rew;
-            if (live) {
-                if (rp.buf_state) {  // replay row (agent_residual.py:64-65; replay.py:278-291), time-major
-                    float *bs = rp.buf_state + q * S;
-                    if (S == 4) *reinterpret_cast<float4 *>(bs) = make_float4(obs[0], obs[1], obs[2], obs[3]);
-                    else for (int k = 0; k < S; ++k) bs[k] = obs[k];
-                    *reinterpret_cast<float4 *>(rp.buf_other + q * 4) =
-                        make_float4((float)((double)rew * rp.reward_scale), done ? 0.0f : (float)rp.gamma, a_raw, eps);
-                }
-                if (rp.env_action) ((T *)rp.env_action)[q] = action;
-                s_rew += (double)rew;
-                s_steps += 1.0;
-                if (done) {
-                    s_ret += (double)env.ret;
-                    s_ret2 += (double)env.ret * (double)env.ret;
-                    s_cnt += 1.0;
-                    s_err += (double)plant.tracking_error(env);
-                }
-            }
-            if (done && rp.auto_reset) {  // env.reset() -> reset_all(): new ensemble member (T4 in SURVEY.md)
-                if (!plant.reset(env, rp.seed, rp.env_offset + (uint64_t)ii)) fault = true;
-                env.ret = (T)0;
+            if (rp.env_action) ((T *)rp.env_action)[q] = action;
+            s_rew += (double)rew;
+            s_steps += 1.0;
+            if (done) {
+                s_ret += (double)env.ret;
+                s_ret2 += (double)env.ret * (double)env.ret;
+                s_cnt += 1.0;
+                s_err += (double)plant.tracking_error(env);
             }
         }
-        if (live) plant.store(env, i, n);
-    } else if (rp.has_actor && (tid & 31) == 0) {
-        if (warp == 4) eng.mma_loop(rp.T);
-        else eng.producer_loop(rp.T);
+        if (done && rp.auto_reset) {  // env.reset() -> reset_all(): new ensemble member (T4 in SURVEY.md)
+            if (!plant.reset(env, rp.seed, rp.env_offset + (uint64_t)ii)) fault = true;
+            env.ret = (T)0;
+        }
     }
 
-    if (rp.has_actor) eng.teardown();
-
-    // ---- warp-shuffle reduction of the episode / set-point statistics, one atomic set per CTA
-    if (rp.stats) {
-        __shared__ double red[6][4];
+    // warp-shuffle reduction of the episode / set-point statistics; lane 0 of each calling warp adds to red[][slot]
+    __device__ __forceinline__ void reduce_warp(double (*red)[4], int slot) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s_ret += __shfl_xor_sync(0xffffffffu, s_ret, o);
@@ -251,28 +231,114 @@ __global__ void __launch_bounds__(tc::kThreads, MINB) rollout_kernel(Plant plant
             s_rew += __shfl_xor_sync(0xffffffffu, s_rew, o);
             s_steps += __shfl_xor_sync(0xffffffffu, s_steps, o);
         }
-        if (warp < 4 && (tid & 31) == 0) {
-            red[0][warp] = s_ret; red[1][warp] = s_ret2; red[2][warp] = s_cnt;
-            red[3][warp] = s_err; red[4][warp] = s_rew; red[5][warp] = s_steps;
+        if ((threadIdx.x & 31) == 0) {
+            red[0][slot] = s_ret; red[1][slot] = s_ret2; red[2][slot] = s_cnt;
+            red[3][slot] = s_err; red[4][slot] = s_rew; red[5][slot] = s_steps;
         }
-        __syncthreads();
-        if (tid < 6) atomicAdd(rp.stats + tid, red[tid][0] + red[tid][1] + red[tid][2] + red[tid][3]);
     }
+};
+
+// ------------------------------------------------------------------------------------------------ the kernels
+// Fused rollout with an actor: 256 envs per CTA (two groups of 128), see tc_mlp.cuh for the roles.
+template <typename Plant, int KIND, int H>
+__global__ void __launch_bounds__(tc::kThreads, 1) rollout_kernel(Plant plant, tc::MlpParams mp, RolloutParams rp) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ double red[6][4];
+    tc::Engine<KIND, H> eng;
+    eng.setup(smem, mp);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int passes = 2 * rp.T;
+    bool fault = false;
+
+    if (warp < 8) {
+        eng.worker_loop(passes);
+    } else if (warp < 12) {
+        const int row = tid - tc::kWorkerThreads;
+        const int64_t n = rp.n;
+        const int64_t i0 = (int64_t)blockIdx.x * tc::kTileEnvs + row, i1 = i0 + tc::kRows;
+        const bool live0 = i0 < n, live1 = i1 < n;
+        const int64_t ii0 = live0 ? i0 : n - 1, ii1 = live1 ? i1 : n - 1;  // tail rows shadow the last env and write nothing
+        typename Plant::Env env0, env1;
+        plant.load(env0, ii0, n);
+        plant.load(env1, ii1, n);
+        Stepper<Plant> sp;
+        float obs[kMaxS];
+        plant.observe(env0, obs);
+        eng.write_obs(row, 0, obs);
+        plant.observe(env1, obs);
+        eng.write_obs(row, 1, obs);
+        for (int s = 0; s < rp.T; ++s) {
+            const bool more = s + 1 < rp.T;
+            {   // group 0: its network pass is 2s; the workers run group 1's pass while this thread steps the plant
+                const float a_avg = eng.read_out(row, 2 * s);
+                plant.observe(env0, obs);
+                sp.step(plant, rp, env0, obs, a_avg, s, ii0, live0);
+                if (more) { plant.observe(env0, obs); eng.write_obs(row, 0, obs); }
+            }
+            {
+                const float a_avg = eng.read_out(row, 2 * s + 1);
+                plant.observe(env1, obs);
+                sp.step(plant, rp, env1, obs, a_avg, s, ii1, live1);
+                if (more) { plant.observe(env1, obs); eng.write_obs(row, 1, obs); }
+            }
+        }
+        if (live0) plant.store(env0, i0, n);
+        if (live1) plant.store(env1, i1, n);
+        fault = sp.fault;
+        if (rp.stats) sp.reduce_warp(red, warp - 8);
+    } else if (warp == tc::kMmaWarp) {
+        eng.mma_loop(passes);
+    } else if ((tid & 31) == 0) {
+        eng.producer_loop(passes);
+    }
+
+    eng.teardown();  // __syncthreads inside: red[][] is complete
+    if (rp.stats && tid < 6) atomicAdd(rp.stats + tid, red[tid][0] + red[tid][1] + red[tid][2] + red[tid][3]);
     if (fault && rp.status) atomicMin(rp.status, (int32_t)PIME_ERANGE);
 }
 
+// Prior-only policy (no actor): one thread per env, nothing but the plant and the prior.
+template <typename Plant>
+__global__ void __launch_bounds__(128) rollout_prior_kernel(Plant plant, RolloutParams rp) {
+    __shared__ double red[6][4];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int64_t n = rp.n;
+    const int64_t i = (int64_t)blockIdx.x * 128 + tid;
+    const bool live = i < n;
+    const int64_t ii = live ? i : n - 1;
+    typename Plant::Env env;
+    plant.load(env, ii, n);
+    Stepper<Plant> sp;
+    float obs[kMaxS];
+    for (int s = 0; s < rp.T; ++s) {
+        plant.observe(env, obs);
+        sp.step(plant, rp, env, obs, 0.0f, s, ii, live);
+    }
+    if (live) plant.store(env, i, n);
+    if (rp.stats) sp.reduce_warp(red, warp);
+    __syncthreads();
+    if (rp.stats && tid < 6) atomicAdd(rp.stats + tid, red[tid][0] + red[tid][1] + red[tid][2] + red[tid][3]);
+    if (sp.fault && rp.status) atomicMin(rp.status, (int32_t)PIME_ERANGE);
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
+template <typename Plant> int launch_rollout_prior(const Plant &plant, const RolloutParams &rp, cudaStream_t stream) {
+    const int64_t grid = (rp.n + 127) / 128;
+    PIME_REQUIRE(grid <= 0x7fffffffLL, "too many envs for one launch");
+    rollout_prior_kernel<Plant><<<(unsigned)grid, 128, 0, stream>>>(plant, rp);
+    PIME_LAUNCH_CHECK();
+    return PIME_OK;
+}
+
 template <typename Plant, int KIND, int H>
 int launch_rollout_kh(const Plant &plant, const tc::PackLayout *L, const void *pack, const RolloutParams &rp, cudaStream_t stream) {
     using G = tc::Geo<KIND, H>;
-    constexpr int MINB = G::SmemBytes <= 113 * 1024 ? 2 : 1;
-    auto kern = rollout_kernel<Plant, KIND, H, MINB>;
-    const int smem = rp.has_actor ? G::SmemBytes : 0;
+    auto kern = rollout_kernel<Plant, KIND, H>;
     PIME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SmemBytes));
-    tc::MlpParams mp = rp.has_actor ? tc::make_mlp_params(*L, pack) : tc::MlpParams{};
-    const int64_t grid = (rp.n + tc::kRows - 1) / tc::kRows;
+    const tc::MlpParams mp = tc::make_mlp_params(*L, pack);
+    const int64_t grid = (rp.n + tc::kTileEnvs - 1) / tc::kTileEnvs;
     PIME_REQUIRE(grid <= 0x7fffffffLL, "too many envs for one launch");
-    kern<<<(unsigned)grid, tc::kThreads, smem, stream>>>(plant, mp, rp);
+    kern<<<(unsigned)grid, tc::kThreads, G::SmemBytes, stream>>>(plant, mp, rp);
     PIME_LAUNCH_CHECK();
     return PIME_OK;
 }

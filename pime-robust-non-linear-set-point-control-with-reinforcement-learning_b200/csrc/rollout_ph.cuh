@@ -26,7 +26,7 @@ int ph_rollout_impl(const pime_ph_config *cfg, const T *table, int64_t n, const 
     g.A = (T *)st->A; g.B = (T *)st->B; g.C = (T *)st->C; g.qww = (T *)st->qww_V; g.qc = (T *)st->qc_V;
     g.ep_return = (T *)st->ep_return; g.t = st->t; g.episode = st->episode;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!rp.has_actor) return launch_rollout_kh<PhGlue<T>, PIME_ACTOR_PLAIN, 32>(g, nullptr, nullptr, rp, s);
+    if (!rp.has_actor) return launch_rollout_prior<PhGlue<T>>(g, rp, s);
     if (args->actor->kind == PIME_ACTOR_MODULAR) {
         PIME_REQUIRE(cfg->integrator_mode != PIME_PH_NO_INTEGRATOR, "the modular actor needs the integrator observation");
         return launch_rollout_k<PhGlue<T>, PIME_ACTOR_MODULAR>(g, &L, args->actor_pack, rp, L.H, s);

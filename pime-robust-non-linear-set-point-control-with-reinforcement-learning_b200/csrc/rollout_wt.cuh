@@ -25,7 +25,7 @@ int wt_rollout_impl(const pime_wt_config *cfg, int64_t n, const pime_wt_state *s
     g.a1 = (T *)st->a1; g.a2 = (T *)st->a2; g.Kp = (T *)st->Kp;
     g.ep_return = (T *)st->ep_return; g.frames = (T *)st->frames; g.t = st->t; g.episode = st->episode;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!rp.has_actor) return launch_rollout_kh<WtGlue<T>, PIME_ACTOR_PLAIN, 32>(g, nullptr, nullptr, rp, s);
+    if (!rp.has_actor) return launch_rollout_prior<WtGlue<T>>(g, rp, s);
     if (args->actor->kind == PIME_ACTOR_MODULAR) {
         PIME_REQUIRE(cfg->obs_mode == PIME_WT_OBS_INTEGRATOR, "the modular actor needs the integrator observation");
         return launch_rollout_k<WtGlue<T>, PIME_ACTOR_MODULAR>(g, &L, args->actor_pack, rp, L.H, s);

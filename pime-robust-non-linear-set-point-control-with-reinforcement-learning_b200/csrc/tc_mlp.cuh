@@ -1,30 +1,32 @@
 // tc_mlp.cuh -- the residual-actor MLP on Blackwell tensor cores (tcgen05 + TMEM + TMA bulk copies), written for
-// the fused rollout: 128 envs per CTA = the M=128 rows of every tcgen05.mma = the 128 TMEM lanes, so that thread r
-// of the CTA owns env r end to end (plant state in registers, its activations in "its" TMEM lane, its row of the A
-// operand in shared memory).  No cross-thread traffic other than the tensor-core operands.
+// the fused rollout.  One CTA per SM works on a tile of 256 envs = two groups of 128 rows; a group's 128 rows are the
+// M=128 rows of every tcgen05.mma = the 128 TMEM lanes.  The CTA is a pipeline of four roles connected by mbarriers only:
 //
-//   warps 0-3 (128 threads) : env threads.  Write the observation operand, run the epilogues
-//                             TMEM -> regs -> tanh/relu -> fp16 A operand of the next layer.
-//   warp 4, lane 0          : MMA issuer.  Interprets the block program of the pack: one or more
-//                             tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=128, K=16) per streamed weight block,
-//                             accumulators in TMEM, tcgen05.commit -> mbarriers.
-//   warp 5, lane 0          : TMA producer.  cp.async.bulk streams the pre-tiled fp16 weight blocks (<= 8 KB) from
-//                             the L2-resident pack through a kStages-deep shared-memory ring.
+//   warps 8-11  (128 threads) : owners.  Thread r owns env r of BOTH groups end to end (plant state in registers):
+//                               observation -> fp16 first-layer operand, later net(obs) from TMEM -> action -> plant step.
+//                               While the workers run the network of one group the owners step the plant of the other.
+//   warps 0-7   (256 threads) : workers.  Two threads per row (even / odd 32-column chunks): the layer epilogues
+//                               TMEM -> regs -> tanh/relu -> fp16 A operand of the next layer, signalled PER CHUNK so
+//                               that the next layer's MMAs run behind the epilogue that feeds them.
+//   warp 12, lane 0           : MMA issuer.  Interprets the block program of the pack: tcgen05.mma.cta_group::1.kind::f16
+//                               (M=128, N<=128, K=16), accumulators ping-pong between two TMEM buffers Da / Db.
+//   warp 13, lane 0           : TMA producer.  cp.async.bulk streams the pre-tiled fp16 weight blocks (<= 8 KB) from
+//                               the L2-resident pack through a deep shared-memory ring (up to 128 KB in flight).
 //
-// EVERY layer runs on the tensor core, so that an env thread spends ~1.7 instructions per hidden activation
-// (tcgen05.ld/32 + MUFU.TANH + F2FP/2 + STS/8) and the kernel is bound by the MUFU pipe:
-//   * first layers (K = 1..30 inputs): the fp32 observation is split into fp16 hi + lo parts and the fp32 weight
-//     into hi + lo parts, A = [in_hi | in_lo | in_hi | 1 1], B = [W_hi | W_hi | W_lo | b_hi b_lo]  (3 terms, ~2^-22
-//     relative: fp32-grade first layer; 2 terms when 3S+2 > 32);
+// EVERY layer runs on the tensor core, so that a worker spends ~1.7 instructions per hidden activation
+// (tcgen05.ld/32 + MUFU.TANH + F2FP/2 + STS/8) and the kernel is bound by the MUFU pipe (16 tanh/clk/SM):
+//   * first layers (1..31 inputs): the fp32 observation is split into fp16 hi + lo parts and the fp32 weight into
+//     hi + lo parts, A = [in_hi | in_lo | in_hi | 1 1], B = [W_hi | W_hi | W_lo | b_hi b_lo]  (3 terms, ~2^-22
+//     relative: an fp32-grade first layer; 2 terms when 3S+2 > 32);
 //   * hidden layers: A = fp16 activations written by the previous epilogue, B = fp16 weights; the bias enters
 //     through one extra K=16 MMA against a constant "ones" operand, B = [b_hi b_lo 0 ...];
-//   * output layer Linear(H -> 1): an N=16 MMA whose row 0 is the weight vector; column 0 of TMEM is net(obs).
+//   * output layer Linear(H -> 1): N=16 MMAs whose row 0 is the weight vector; one TMEM column is net(obs).
 //
-// Layers (reference elegantrl/net_residual.py):
-//   modular (:138-205): P0 other_net.0 -> D[0:H];  P1 other_net.2 -> D[0:H/2], integrator_net.0 (units 0..H/2) ->
-//                       D[H/2:H];  P2 integrator_net.0 (units H/2..H) -> D[H/2:H];  P3 integrator_net.2 -> D[H/2:H];
-//                       P4 net.0 on cat(D[0:H]) -> D[0:H];  P5 net.2 -> D[0:16].
-//   plain (:6-66) / CriticAdv (net.py:274-277): P0 net.0, P1 net.2, P2 net.4, P3 net.6.
+// Layers (reference elegantrl/net_residual.py), Da = TMEM columns [0,H), Db = [H,2H):
+//   modular (:138-205): P0 other_net.0 -> Da, integrator_net.0 -> Db;  P1 other_net.2 -> Da[0:H/2] (behind the epilogue
+//                       of Da);  P2 integrator_net.2 -> Da[H/2:H] (behind the epilogue of Db);  P3 net.0 on
+//                       cat = Da -> Db;  P4 net.2 -> Da[0:16].
+//   plain (:6-66) / CriticAdv (net.py:274-277): P0 net.0 -> Da, P1 net.2 -> Db, P2 net.4 -> Da, P3 net.6 -> Db[0:16].
 #pragma once
 
 #include "pime_common.cuh"
@@ -32,19 +34,32 @@
 namespace pime {
 namespace tc {
 
-constexpr int kRows = 128;
-constexpr int kEnvThreads = 128;
-constexpr int kThreads = 192;
-constexpr int kStages = 4;
+constexpr int kRows = 128;              // rows of one group = TMEM lanes
+constexpr int kTileEnvs = 2 * kRows;    // envs per CTA
+constexpr int kWorkerThreads = 256;
+constexpr int kOwnerThreads = 128;
+constexpr int kThreads = 448;           // 8 worker warps + 4 owner warps + MMA warp + TMA warp
+constexpr int kMmaWarp = 12, kTmaWarp = 13;
+constexpr int kMaxStages = 16;
 constexpr int kMaxBlkBytes = 8192;
 constexpr int kChunkBytes = kRows * 16;    // one K core-matrix column (8 fp16) for all 128 rows = 2048 B
 constexpr int kK16Bytes = 2 * kChunkBytes; // one K=16 slice of an A operand = 4096 B
 constexpr int kMaxBlocks = 56;
 constexpr int kHeaderBytes = 1024;         // the block program at the head of the pack (kMaxBlocks x 16 B)
-constexpr int kMaxKP = 80;                 // widest first-layer operand: 2 x 32 inputs + 2 -> 80
+constexpr int kMaxKP = 64;                 // widest first-layer operand (2 x 31 inputs + 2)
+constexpr int kMaxChunks = 8;              // 32-column chunks of a layer (H <= 256)
 
 // ------------------------------------------------------------------------------------------------ block program
-enum : uint32_t { BLK_FRESH = 1u, BLK_WAIT_A = 2u, BLK_COMMIT_D = 4u };
+enum : uint32_t {
+    BLK_FRESH = 1u,       // first MMA of the block overwrites the accumulator
+    BLK_WAIT_OBS = 2u,    // first block of a pass: wait for the group's observation operand (and the previous output read)
+    BLK_COMMIT_D = 4u,    // tcgen05.commit -> d_ready after the block (a TMEM buffer is complete)
+    BLK_PHASE_END = 8u,   // forget which chunk barriers were waited on
+    BLK_FREE = 16u,       // tcgen05.commit -> a_free[chunk] after the block (the A chunk may be overwritten)
+    BLK_OBS_A = 32u,      // A operand is the observation operand of the current group
+    BLK_OUT = 64u         // tcgen05.commit -> out_rdy (net(obs) is in TMEM)
+};
+// flags bits 8..15: chunk barriers a_rdy[j] to wait on before the block; bits 16..18: chunk index for BLK_FREE
 
 struct Blk {             // one streamed weight block = k16s MMAs of shape 128 x (8*nb8) x 16
     uint32_t src_off;    // byte offset inside the fp16 section of the pack
@@ -69,8 +84,9 @@ struct BlkSrc {          // how pack_kernel fills the block from the fp32 state_
 
 __host__ __device__ constexpr int geo_acols(int H) { return H < 64 ? 64 : H; }
 __host__ __device__ constexpr int geo_abytes(int H) { return kRows * geo_acols(H) * 2; }
-__host__ __device__ constexpr int geo_obs_off(int kind, int H) { return kind == PIME_ACTOR_MODULAR ? geo_abytes(H) : 0; }
-__host__ __device__ constexpr int geo_ones_off(int kind, int H) { return geo_abytes(H) + (kind == PIME_ACTOR_MODULAR ? kK16Bytes : 0); }
+__host__ __device__ constexpr int geo_obs_group_bytes(int kind) { return kind == PIME_ACTOR_MODULAR ? kK16Bytes : kRows * kMaxKP * 2; }
+__host__ __device__ constexpr int geo_obs_off(int H) { return geo_abytes(H); }
+__host__ __device__ constexpr int geo_ones_off(int kind, int H) { return geo_abytes(H) + 2 * geo_obs_group_bytes(kind); }
 
 struct PackLayout {
     int kind, H, S, D;
@@ -85,13 +101,17 @@ struct PackLayout {
 
 struct GemmSpec {
     int type, N, n_real, n0, K16, a_off, d_col, w_off, ld, b_off, c0, cN;
+    uint32_t flags;        // extra flags for every block
+    uint32_t first_wait;   // chunk mask the first block waits on (accumulator aliasing lag)
 };
 
 inline bool emit_gemm(PackLayout &L, const GemmSpec &g) {
     const int NB = g.N < 128 ? g.N : 128, nbn = g.N / NB;
     int kpb = kMaxBlkBytes / (NB * 32);
+    if (g.type == SRC_HID && kpb > 2) kpb = 2;   // hidden layers: one block per 32-column chunk of the A operand
     if (kpb < 1) kpb = 1;
     if (kpb > g.K16) kpb = g.K16;
+    bool first = true;
     for (int k = 0; k < g.K16; k += kpb) {
         const int kk = g.K16 - k < kpb ? g.K16 - k : kpb;
         for (int nb = 0; nb < nbn; ++nb) {
@@ -104,13 +124,21 @@ inline bool emit_gemm(PackLayout &L, const GemmSpec &g) {
             b.k16s = (uint8_t)kk;
             b.a_off16 = (uint16_t)((g.a_off + k * kK16Bytes) / 16);
             b.d_col = (uint16_t)(g.d_col + nb * NB);
-            b.flags = k == 0 ? BLK_FRESH : 0u;
+            b.flags = g.flags | (k == 0 && g.type != SRC_HID ? BLK_FRESH : 0u);
+            if (first) b.flags |= g.first_wait << 8;
+            if (g.type == SRC_HID) {
+                const int chunk = k / 2;                       // K=32 per chunk
+                b.flags |= (1u << chunk) << 8;
+                if (kk > 2) return false;
+                if ((g.flags & BLK_FREE) && nb == nbn - 1) b.flags |= (uint32_t)chunk << 16; else b.flags &= ~BLK_FREE;
+            }
             s.type = g.type; s.w_off = g.w_off; s.ld = g.ld; s.b_off = g.b_off;
             s.n0 = g.n0 + nb * NB;
             s.n_real = g.n_real - nb * NB;
             s.k0 = k * 16; s.c0 = g.c0; s.cN = g.cN;
             L.f16_bytes += NB * kk * 32;
             ++L.nblk;
+            first = false;
         }
     }
     return true;
@@ -124,24 +152,18 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
     L = PackLayout{};
     L.kind = c.kind; L.H = H; L.S = S; L.D = D;
     const int Hh = H / 2, HK = H / 16;
-    const int a_obs = geo_obs_off(c.kind, H), a_ones = geo_ones_off(c.kind, H);
+    const int a_obs = geo_obs_off(H), a_ones = geo_ones_off(c.kind, H);
+    const int Da = 0, Db = H;
     bool ok = true;
-    int first = 0;
-    auto phase_end = [&]() {
-        L.blk[first].flags |= BLK_WAIT_A;
-        L.blk[L.nblk - 1].flags |= BLK_COMMIT_D;
-        first = L.nblk;
+    auto end = [&](uint32_t f) { L.blk[L.nblk - 1].flags |= f | BLK_PHASE_END; };
+    auto bias = [&](int N, int n_real, int b_off, int d_col, uint32_t first_wait) {
+        ok = ok && emit_gemm(L, GemmSpec{SRC_BIAS, N, n_real, 0, 1, a_ones, d_col, 0, 0, b_off, 0, 0, 0u, first_wait});
     };
-    auto bias = [&](int N, int n_real, int b_off, int d_col) {
-        ok = ok && emit_gemm(L, GemmSpec{SRC_BIAS, N, n_real, 0, 1, a_ones, d_col, 0, 0, b_off, 0, 0});
+    auto hid = [&](int N, int n_real, int w_off, int d_col, uint32_t flags) {   // accumulates on top of the bias block
+        ok = ok && emit_gemm(L, GemmSpec{SRC_HID, N, n_real, 0, HK, 0, d_col, w_off, H, 0, 0, 0, flags, 0u});
     };
-    auto hid = [&](int N, int n_real, int w_off, int d_col) {   // accumulates on top of the bias block
-        const int nb0 = L.nblk;
-        ok = ok && emit_gemm(L, GemmSpec{SRC_HID, N, n_real, 0, HK, 0, d_col, w_off, H, 0, 0, 0});
-        for (int j = nb0; j < L.nblk; ++j) L.blk[j].flags &= ~BLK_FRESH;
-    };
-    auto l1 = [&](int N, int n0, int w_off, int ld, int b_off, int c0, int cN, int d_col) {
-        ok = ok && emit_gemm(L, GemmSpec{SRC_L1, N, N, n0, L.KP / 16, a_obs, d_col, w_off, ld, b_off, c0, cN});
+    auto l1 = [&](int N, int w_off, int ld, int b_off, int c0, int cN, int d_col) {
+        ok = ok && emit_gemm(L, GemmSpec{SRC_L1, N, N, 0, L.KP / 16, a_obs, d_col, w_off, ld, b_off, c0, cN, BLK_OBS_A, 0u});
     };
     if (c.kind == PIME_ACTOR_MODULAR) {
         const int So = S - D;
@@ -153,13 +175,13 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
         for (int j = 0; j < 12; ++j) { L.src[j] = o; o += sizes[j]; }
         L.param_count = o;
         L.nin = 4; L.nterms = 3; L.KP = 16;   // inputs (o0,o1,o2,I): 3 x 4 + 2 = 14 <= 16
-        l1(H, 0, L.src[0], So, L.src[1], 0, So, 0);                     phase_end();  // P0 other_net.0
-        bias(Hh, Hh, L.src[3], 0); hid(Hh, Hh, L.src[2], 0);                          // P1 other_net.2
-        l1(Hh, 0, L.src[4], 1, L.src[5], 3, 1, Hh);                     phase_end();  //    integrator_net.0, units [0,H/2)
-        l1(Hh, Hh, L.src[4], 1, L.src[5], 3, 1, Hh);                    phase_end();  // P2 integrator_net.0, units [H/2,H)
-        bias(Hh, Hh, L.src[7], Hh); hid(Hh, Hh, L.src[6], Hh);          phase_end();  // P3 integrator_net.2
-        bias(H, H, L.src[9], 0); hid(H, H, L.src[8], 0);                phase_end();  // P4 net.0
-        bias(16, 1, L.src[11], 0); hid(16, 1, L.src[10], 0);            phase_end();  // P5 net.2
+        const uint32_t lag = (1u << ((Hh + 31) / 32)) - 1u;   // chunks of Da that must be consumed before Da[0:H/2] is reused
+        l1(H, L.src[0], So, L.src[1], 0, So, Da);                                       // P0 other_net.0 -> Da
+        l1(H, L.src[4], 1, L.src[5], 3, 1, Db);                      end(BLK_COMMIT_D);  //    integrator_net.0 -> Db
+        bias(Hh, Hh, L.src[3], Da, lag); hid(Hh, Hh, L.src[2], Da, BLK_FREE);  end(0);   // P1 other_net.2 -> Da[0:H/2]
+        bias(Hh, Hh, L.src[7], Da + Hh, 0); hid(Hh, Hh, L.src[6], Da + Hh, 0); end(BLK_COMMIT_D);  // P2 integrator_net.2
+        bias(H, H, L.src[9], Db, 0); hid(H, H, L.src[8], Db, 0);     end(BLK_COMMIT_D);  // P3 net.0 -> Db
+        bias(16, 1, L.src[11], Da, 0); hid(16, 1, L.src[10], Da, 0); end(BLK_COMMIT_D | BLK_OUT);  // P4 net.2 -> Da[0:16]
     } else {
         // state_dict order: net.0.{w,b} net.2.{w,b} net.4.{w,b} net.6.{w,b}
         const int sizes[8] = {H * S, H, H * H, H, H * H, H, H, 1};
@@ -169,13 +191,14 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
         L.nin = S;
         L.nterms = 3 * S + 2 <= 32 ? 3 : 2;
         L.KP = ((L.nterms * S + 2 + 15) / 16) * 16;
-        if (L.KP * kRows * 2 > geo_abytes(H)) return false;  // the observation operand aliases the A tile
-        l1(H, 0, L.src[0], S, L.src[1], 0, S, 0);                       phase_end();  // P0 net.0
-        bias(H, H, L.src[3], 0); hid(H, H, L.src[2], 0);                phase_end();  // P1 net.2
-        bias(H, H, L.src[5], 0); hid(H, H, L.src[4], 0);                phase_end();  // P2 net.4
-        bias(16, 1, L.src[7], 0); hid(16, 1, L.src[6], 0);              phase_end();  // P3 net.6
+        if (L.KP > kMaxKP) return false;
+        l1(H, L.src[0], S, L.src[1], 0, S, Da);                      end(BLK_COMMIT_D);  // P0 net.0 -> Da
+        bias(H, H, L.src[3], Db, 0); hid(H, H, L.src[2], Db, 0);     end(BLK_COMMIT_D);  // P1 net.2 -> Db
+        bias(H, H, L.src[5], Da, 0); hid(H, H, L.src[4], Da, 0);     end(BLK_COMMIT_D);  // P2 net.4 -> Da
+        bias(16, 1, L.src[7], Db, 0); hid(16, 1, L.src[6], Db, 0);   end(BLK_COMMIT_D | BLK_OUT);  // P3 net.6 -> Db[0:16]
     }
     if (!ok) return false;
+    L.blk[0].flags |= BLK_WAIT_OBS;
     L.total_bytes = kHeaderBytes + L.f16_bytes;
     return true;
 }
@@ -196,15 +219,18 @@ inline MlpParams make_mlp_params(const PackLayout &L, const void *pack) {
 template <int KIND, int H> struct Geo {
     static constexpr bool kModular = KIND == PIME_ACTOR_MODULAR;
     static constexpr bool kRelu = KIND == PIME_CRITIC_ADV;
-    static constexpr int Hh = H / 2;
+    static constexpr int NCh = H / 32 < 1 ? 1 : H / 32;      // 32-column chunks per layer
     static constexpr int ABytes = geo_abytes(H);
-    static constexpr int ObsOff = geo_obs_off(KIND, H);
+    static constexpr int ObsOff = geo_obs_off(H);
+    static constexpr int ObsGroupBytes = geo_obs_group_bytes(KIND);
     static constexpr int OnesOff = geo_ones_off(KIND, H);
     static constexpr int RingOff = OnesOff + kK16Bytes;
-    static constexpr int TblOff = RingOff + kStages * kMaxBlkBytes;
+    static constexpr int Stages = kModular ? 16 : 13;
+    static constexpr int TblOff = RingOff + Stages * kMaxBlkBytes;
     static constexpr int BarOff = TblOff + kMaxBlocks * 16;
-    static constexpr int SmemBytes = BarOff + 128;
-    static constexpr int TmemCols = H < 32 ? 32 : H;
+    static constexpr int SmemBytes = BarOff + 512;
+    static constexpr int TmemCols = 2 * H < 32 ? 32 : 2 * H;
+    static constexpr int OutCol = kModular ? 0 : H;          // TMEM column of net(obs)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -271,6 +297,13 @@ __device__ __forceinline__ void mma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// one lane of a converged warp (the CUTLASS elect_one_sync idiom: keeps the tcgen05 operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread t of warp w gets row 32*(w%4)+t
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t *u = reinterpret_cast<uint32_t *>(v);
@@ -330,14 +363,27 @@ __device__ __forceinline__ void split_h(float x, __half &hi, __half &lo) {
 }
 
 // ------------------------------------------------------------------------------------------------ the engine
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) {
+    uint32_t *u = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+          "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+          "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+          "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 template <int KIND, int H> struct Engine {
     using G = Geo<KIND, H>;
     uint8_t *sA, *sRing;
     const Blk *tbl;
-    uint64_t *full, *empty, *a_ready, *d_ready;
+    uint64_t *full, *empty, *a_rdy, *a_free, *o_rdy, *d_ready, *out_rdy, *out_read;
     uint32_t *tmem_slot;
     uint32_t tmem_base;
-    uint32_t dph;  // parity of the next d_ready completion (env threads)
     MlpParams mp;
 
     // All kThreads threads.  Carves shared memory, initialises barriers, allocates TMEM, loads the block program and
@@ -348,19 +394,26 @@ template <int KIND, int H> struct Engine {
         sRing = smem + G::RingOff;
         tbl = reinterpret_cast<const Blk *>(smem + G::TblOff);
         full = reinterpret_cast<uint64_t *>(smem + G::BarOff);
-        empty = full + kStages;
-        a_ready = empty + kStages;
-        d_ready = a_ready + 1;
-        tmem_slot = reinterpret_cast<uint32_t *>(d_ready + 1);
-        dph = 0;
+        empty = full + kMaxStages;
+        a_rdy = empty + kMaxStages;
+        a_free = a_rdy + kMaxChunks;
+        o_rdy = a_free + kMaxChunks;
+        d_ready = o_rdy + 2;
+        out_rdy = d_ready + 1;
+        out_read = out_rdy + 1;
+        tmem_slot = reinterpret_cast<uint32_t *>(out_read + 1);
         const int tid = threadIdx.x;
         if (tid == 0) {
-            for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-            mbar_init(a_ready, kEnvThreads);
+            for (int s = 0; s < G::Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            for (int j = 0; j < kMaxChunks; ++j) { mbar_init(&a_rdy[j], kRows); mbar_init(&a_free[j], 1); }
+            mbar_init(&o_rdy[0], kOwnerThreads);
+            mbar_init(&o_rdy[1], kOwnerThreads);
             mbar_init(d_ready, 1);
+            mbar_init(out_rdy, 1);
+            mbar_init(out_read, kOwnerThreads);
             fence_barrier_init();
         }
-        if (tid / 32 == 4) tmem_alloc(tmem_slot, G::TmemCols);
+        if (tid / 32 == kMmaWarp) tmem_alloc(tmem_slot, G::TmemCols);
         const uint4 *src = reinterpret_cast<const uint4 *>(mp.pack);
         uint4 *dst = reinterpret_cast<uint4 *>(smem + G::TblOff);
         for (int j = tid; j < mp.nblk; j += kThreads) dst[j] = __ldg(src + j);
@@ -377,110 +430,222 @@ template <int KIND, int H> struct Engine {
     __device__ __forceinline__ void teardown() {
         tc_fence_before();
         __syncthreads();
-        if (threadIdx.x / 32 == 4) tmem_dealloc(tmem_base, G::TmemCols);
+        if (threadIdx.x / 32 == kMmaWarp) tmem_dealloc(tmem_base, G::TmemCols);
     }
 
-    // ---- warp 5 lane 0: stream every weight block of every step through the ring
-    __device__ __forceinline__ void producer_loop(int steps) {
+    // ---- TMA warp, lane 0: stream every weight block of every pass through the ring
+    __device__ __forceinline__ void producer_loop(int passes) {
         const uint8_t *w16 = mp.pack + kHeaderBytes;
         const int nblk = mp.nblk;
-        uint32_t it = 0;
-        for (int s = 0; s < steps; ++s) {
-            for (int b = 0; b < nblk; ++b, ++it) {
+        uint32_t st = 0, ph = 0;
+        for (int q = 0; q < passes; ++q) {
+            for (int b = 0; b < nblk; ++b) {
                 const Blk B = tbl[b];
-                const uint32_t st = it % kStages, ph = (it / kStages) & 1;
                 const uint32_t bytes = (uint32_t)B.bytes16 * 16u;
                 mbar_wait(&empty[st], ph ^ 1);
                 mbar_arrive_expect_tx(&full[st], bytes);
                 bulk_g2s(sRing + st * kMaxBlkBytes, w16 + B.src_off, bytes, &full[st]);
+                if (++st == (uint32_t)G::Stages) { st = 0; ph ^= 1; }
             }
         }
     }
 
-    // ---- warp 4 lane 0: interpret the block program, once per step
-    __device__ __forceinline__ void mma_loop(int steps) {
-        const int nblk = mp.nblk;
-        uint32_t it = 0, aph = 0;
-        const uint32_t a_base = smem_u32(sA);
-        for (int s = 0; s < steps; ++s) {
-            for (int b = 0; b < nblk; ++b, ++it) {
-                const Blk B = tbl[b];
-                if (B.flags & BLK_WAIT_A) {
-                    mbar_wait(a_ready, aph);
-                    aph ^= 1;
-                    tc_fence_after();
-                }
-                const uint32_t st = it % kStages, ph = (it / kStages) & 1;
-                mbar_wait(&full[st], ph);
+    // ---- MMA warp (all 32 lanes, convergent; one elected lane issues): the static program of the network, once per
+    // pass (pass q works on group q & 1).  The block order is exactly the order make_pack_layout() emits, which is
+    // the order the producer streams.  Everything but the ring stage is a compile-time constant, so a block costs a
+    // barrier poll, the tcgen05.mma instructions and one commit.
+    uint32_t m_st, m_ph;     // ring stage / parity (MMA warp)
+    uint64_t adesc_base;     // descriptor of the operand area start (A tile, observation and ones operands share LBO/SBO)
+
+    template <int N, bool FRESH>
+    __device__ __forceinline__ void blk(uint32_t a_off, int k16s, uint32_t d_col, uint64_t *x1 = nullptr, uint64_t *x2 = nullptr) {
+        mbar_wait(&full[m_st], m_ph);
+        tc_fence_after();
+        if (elect_one()) {
+            const uint32_t b_addr = smem_u32(sRing) + m_st * kMaxBlkBytes;
+            constexpr uint32_t idesc = make_idesc(kRows, N);
+            for (int kk = 0; kk < k16s; ++kk) {
+                const uint64_t adesc = adesc_base + (uint64_t)((a_off + (uint32_t)kk * kK16Bytes) >> 4);
+                const uint64_t bdesc = make_desc(b_addr + (uint32_t)kk * 2u * (N * 16), N * 16, 128);
+                mma_f16(tmem_base + d_col, adesc, bdesc, idesc, (FRESH && kk == 0) ? 0u : 1u);
+            }
+            mma_commit(&empty[m_st]);  // frees the ring slot once these MMAs have read it
+            if (x1) mma_commit(x1);
+            if (x2) mma_commit(x2);
+        }
+        __syncwarp();
+        if (++m_st == (uint32_t)G::Stages) { m_st = 0; m_ph ^= 1; }
+    }
+
+    __device__ __forceinline__ void mma_loop(int passes) {
+        constexpr int NB = H < 128 ? H : 128, nbn = H / NB, Hh = H / 2, NCh = G::NCh;
+        constexpr uint32_t Da = 0, Db = H, ones = G::OnesOff;
+        m_st = 0; m_ph = 0;
+        adesc_base = make_desc(smem_u32(sA), kChunkBytes, 128);
+        uint32_t apar = 0;   // parity of the next completion of the chunk barriers (all chunks complete once per epilogue)
+        for (int q = 0; q < passes; ++q) {
+            const uint32_t g = (uint32_t)q & 1u;
+            const uint32_t obs = (uint32_t)G::ObsOff + g * (uint32_t)G::ObsGroupBytes;
+            mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);            // the group's observation operand is written
+            if (q > 0) mbar_wait(out_read, ((uint32_t)q - 1u) & 1u);   // the previous pass's output column has been read
+            tc_fence_after();
+            if constexpr (G::kModular) {
+                constexpr int lag = (Hh + 31) / 32;   // chunks of Da to be consumed before Da[0:H/2] is overwritten
+                // P0: other_net.0 -> Da, integrator_net.0 -> Db
+#pragma unroll
+                for (int nb = 0; nb < nbn; ++nb) blk<NB, true>(obs, 1, Da + nb * NB);
+#pragma unroll
+                for (int nb = 0; nb < nbn; ++nb) blk<NB, true>(obs, 1, Db + nb * NB, nb == nbn - 1 ? d_ready : nullptr);
+                // P1: other_net.2 -> Da[0:H/2], behind the epilogue of Da
+#pragma unroll
+                for (int j = 0; j < lag; ++j) mbar_wait(&a_rdy[j], apar);
                 tc_fence_after();
-                const uint32_t nbytes16 = (uint32_t)B.nb8 * 8u * 16u;  // bytes of one K core-matrix column of B
-                const uint32_t idesc = make_idesc(kRows, (int)B.nb8 * 8);
-                const uint32_t b_base = smem_u32(sRing + st * kMaxBlkBytes);
-                const uint32_t a_addr = a_base + (uint32_t)B.a_off16 * 16u;
-                const uint32_t d_addr = tmem_base + (uint32_t)B.d_col;
-                const uint32_t k16s = B.k16s;
-                uint32_t acc = (B.flags & BLK_FRESH) ? 0u : 1u;
-                for (uint32_t kk = 0; kk < k16s; ++kk) {
-                    const uint64_t adesc = make_desc(a_addr + kk * kK16Bytes, kChunkBytes, 128);
-                    const uint64_t bdesc = make_desc(b_base + kk * 2u * nbytes16, nbytes16, 128);
-                    mma_f16(d_addr, adesc, bdesc, idesc, acc);
-                    acc = 1u;
+                blk<Hh, true>(ones, 1, Da);
+#pragma unroll
+                for (int j = 0; j < NCh; ++j) {
+                    if (j >= lag) { mbar_wait(&a_rdy[j], apar); tc_fence_after(); }
+                    blk<Hh, false>(j * 2 * kK16Bytes, 2, Da, &a_free[j]);
                 }
-                mma_commit(&empty[st]);  // frees the ring slot once these MMAs have read it
-                if (B.flags & BLK_COMMIT_D) mma_commit(d_ready);  // accumulators of this phase complete, A free again
+                apar ^= 1;
+                // P2: integrator_net.2 -> Da[H/2:H], behind the epilogue of Db
+                blk<Hh, true>(ones, 1, Da + Hh);
+#pragma unroll
+                for (int j = 0; j < NCh; ++j) {
+                    mbar_wait(&a_rdy[j], apar);
+                    tc_fence_after();
+                    blk<Hh, false>(j * 2 * kK16Bytes, 2, Da + Hh, j == NCh - 1 ? d_ready : nullptr);
+                }
+                apar ^= 1;
+                // P3: net.0 on cat -> Db
+#pragma unroll
+                for (int nb = 0; nb < nbn; ++nb) blk<NB, true>(ones, 1, Db + nb * NB);
+#pragma unroll
+                for (int j = 0; j < NCh; ++j) {
+                    mbar_wait(&a_rdy[j], apar);
+                    tc_fence_after();
+#pragma unroll
+                    for (int nb = 0; nb < nbn; ++nb)
+                        blk<NB, false>(j * 2 * kK16Bytes, 2, Db + nb * NB, (j == NCh - 1 && nb == nbn - 1) ? d_ready : nullptr);
+                }
+                apar ^= 1;
+                // P4: net.2 -> Da[0:16]
+                blk<16, true>(ones, 1, Da);
+#pragma unroll
+                for (int j = 0; j < NCh; ++j) {
+                    mbar_wait(&a_rdy[j], apar);
+                    tc_fence_after();
+                    blk<16, false>(j * 2 * kK16Bytes, 2, Da, j == NCh - 1 ? d_ready : nullptr, j == NCh - 1 ? out_rdy : nullptr);
+                }
+                apar ^= 1;
+            } else {
+                // P0: net.0 -> Da (first-layer operand K = KP)
+                const int K16 = mp.KP / 16;
+                constexpr int kpb = kMaxBlkBytes / (NB * 32);
+                for (int k = 0; k < K16; k += kpb) {
+                    const int kk = K16 - k < kpb ? K16 - k : kpb;
+                    const bool last_k = k + kpb >= K16;
+#pragma unroll
+                    for (int nb = 0; nb < nbn; ++nb) {
+                        uint64_t *x = (last_k && nb == nbn - 1) ? d_ready : nullptr;
+                        if (k == 0) blk<NB, true>(obs, kk, Da + nb * NB, x);
+                        else blk<NB, false>(obs + (uint32_t)k * kK16Bytes, kk, Da + nb * NB, x);
+                    }
+                }
+                // P1: net.2 -> Db;  P2: net.4 -> Da
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    const uint32_t d = p == 0 ? Db : Da;
+#pragma unroll
+                    for (int nb = 0; nb < nbn; ++nb) blk<NB, true>(ones, 1, d + nb * NB);
+#pragma unroll
+                    for (int j = 0; j < NCh; ++j) {
+                        mbar_wait(&a_rdy[j], apar);
+                        tc_fence_after();
+#pragma unroll
+                        for (int nb = 0; nb < nbn; ++nb)
+                            blk<NB, false>(j * 2 * kK16Bytes, 2, d + nb * NB, (j == NCh - 1 && nb == nbn - 1) ? d_ready : nullptr);
+                    }
+                    apar ^= 1;
+                }
+                // P3: net.6 -> Db[0:16]
+                blk<16, true>(ones, 1, Db);
+#pragma unroll
+                for (int j = 0; j < NCh; ++j) {
+                    mbar_wait(&a_rdy[j], apar);
+                    tc_fence_after();
+                    blk<16, false>(j * 2 * kK16Bytes, 2, Db, j == NCh - 1 ? d_ready : nullptr, j == NCh - 1 ? out_rdy : nullptr);
+                }
+                apar ^= 1;
             }
         }
     }
 
-    // ---- env threads
+    // ---- workers (warps 0-7): thread (row, half) runs the epilogue of the even (half 0) / odd (half 1) chunks
     __device__ __forceinline__ void a_store8(int row, int kchunk, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3) {
         *reinterpret_cast<uint4 *>(sA + (size_t)kchunk * kChunkBytes + row * 16) = make_uint4(p0, p1, p2, p3);
     }
-    __device__ __forceinline__ void signal_a() {
-        tc_fence_before();
-        fence_proxy_async();
-        mbar_arrive(a_ready);
-    }
-    __device__ __forceinline__ void wait_d() {
-        mbar_wait(d_ready, dph);
-        dph ^= 1;
-        tc_fence_after();
-    }
-
-    // epilogue of a layer: A[:, acol + c] = act(D[:, dcol + c]) for c in [0, ncols); the bias is already in D
-    template <int NCOLS> __device__ __forceinline__ void epilogue_to_a(int row, int dcol, int acol) {
+    // A[:, 32j .. 32j+32) = act(D[:, dcol + 32j ..)) for the chunks j of this half; the bias is already in D.
+    // WAIT_FREE: the previous reader of A chunk j is still in flight (no d_ready wait in between): wait a_free[j].
+    template <bool WAIT_FREE> __device__ __forceinline__ void epilogue(int row, int half, int dcol, uint32_t free_parity) {
         const uint32_t taddr = tmem_base + ((uint32_t)((row / 32) * 32) << 16) + (uint32_t)dcol;
-        if constexpr (NCOLS % 32 == 0) {
-#pragma unroll 2
-            for (int c0 = 0; c0 < NCOLS; c0 += 32) {
-                float v[32];
-                tmem_ld32(taddr + c0, v);
+        constexpr int W = H < 32 ? H : 32;   // chunk width
+        float v[2][32];
+        if (half < G::NCh) tmem_ld32_issue(taddr + half * 32, v[0]);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = act_fn<G::kRelu>(v[j]);
+        for (int it = 0; it < (G::NCh + 1) / 2; ++it) {
+            const int j = half + 2 * it;
+            if (j < G::NCh) {
+                tmem_wait_ld();
+                if (j + 2 < G::NCh) tmem_ld32_issue(taddr + (j + 2) * 32, v[(it + 1) & 1]);
+                float(&x)[32] = v[it & 1];
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    a_store8(row, (acol + c0) / 8 + q, pack_h2(v[q * 8 + 0], v[q * 8 + 1]), pack_h2(v[q * 8 + 2], v[q * 8 + 3]),
-                             pack_h2(v[q * 8 + 4], v[q * 8 + 5]), pack_h2(v[q * 8 + 6], v[q * 8 + 7]));
-            }
-        } else {
-            static_assert(NCOLS % 16 == 0, "layer width");
+                for (int e = 0; e < W; ++e) x[e] = act_fn<G::kRelu>(x[e]);
+                if (WAIT_FREE) mbar_wait(&a_free[j], free_parity);
 #pragma unroll
-            for (int c0 = 0; c0 < NCOLS; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + c0, v);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = act_fn<G::kRelu>(v[j]);
-#pragma unroll
-                for (int q = 0; q < 2; ++q)
-                    a_store8(row, (acol + c0) / 8 + q, pack_h2(v[q * 8 + 0], v[q * 8 + 1]), pack_h2(v[q * 8 + 2], v[q * 8 + 3]),
-                             pack_h2(v[q * 8 + 4], v[q * 8 + 5]), pack_h2(v[q * 8 + 6], v[q * 8 + 7]));
+                for (int qd = 0; qd < W / 8; ++qd)
+                    a_store8(row, j * 4 + qd, pack_h2(x[qd * 8 + 0], x[qd * 8 + 1]), pack_h2(x[qd * 8 + 2], x[qd * 8 + 3]),
+                             pack_h2(x[qd * 8 + 4], x[qd * 8 + 5]), pack_h2(x[qd * 8 + 6], x[qd * 8 + 7]));
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(&a_rdy[j]);
             }
         }
     }
 
+    __device__ __forceinline__ void worker_loop(int passes) {
+        const int tid = threadIdx.x, row = tid & (kRows - 1), half = tid >> 7;
+        uint32_t dph = 0;
+        auto wait_d = [&]() {
+            mbar_wait(d_ready, dph);
+            dph ^= 1;
+            tc_fence_after();
+        };
+        for (int q = 0; q < passes; ++q) {
+            if constexpr (G::kModular) {
+                wait_d();                                             // P0: Da = other_net.0, Db = integrator_net.0 (net_residual.py:151,154)
+                epilogue<false>(row, half, 0, 0);                     // tanh(Da) -> A, feeds other_net.2 (:152)
+                epilogue<true>(row, half, H, (uint32_t)q & 1u);       // tanh(Db) -> A, feeds integrator_net.2 (:155)
+                wait_d();                                             // P2: Da = cat pre-activation (:170)
+                epilogue<false>(row, half, 0, 0);                     // feeds net.0 (:157)
+                wait_d();                                             // P3: Db = net.0
+                epilogue<false>(row, half, H, 0);                     // feeds net.2 (:158)
+                wait_d();                                             // P4 (the owners read the output column)
+            } else {
+                wait_d();
+                epilogue<false>(row, half, 0, 0);
+                wait_d();
+                epilogue<false>(row, half, H, 0);
+                wait_d();
+                epilogue<false>(row, half, 0, 0);
+                wait_d();
+            }
+        }
+    }
+
+    // ---- owners (warps 8-11): thread r owns row r of both groups
     // first-layer operand of this env: [in_hi | in_lo | in_hi (3 terms) | 1 1 | 0 ...]  (see the file header)
-    __device__ __forceinline__ void write_obs(int row, const float *obs) {
-        uint8_t *dst = sA + G::ObsOff + row * 16;
+    __device__ __forceinline__ void write_obs(int row, int g, const float *obs) {
+        uint8_t *dst = sA + G::ObsOff + g * G::ObsGroupBytes + row * 16;
         if constexpr (G::kModular) {
             const int So = mp.S - 1;
             __half h[4], l[4];
@@ -507,48 +672,19 @@ template <int KIND, int H> struct Engine {
             }
             hl[nt * S] = __float2half_rn(1.0f);
             hl[nt * S + 1] = __float2half_rn(1.0f);
-            const uint4 *q = reinterpret_cast<const uint4 *>(hl);
-            for (int kc = 0; kc < KP / 8; ++kc) *reinterpret_cast<uint4 *>(dst + (size_t)kc * kChunkBytes) = q[kc];
+            const uint4 *qv = reinterpret_cast<const uint4 *>(hl);
+            for (int kc = 0; kc < KP / 8; ++kc) *reinterpret_cast<uint4 *>(dst + (size_t)kc * kChunkBytes) = qv[kc];
         }
+        fence_proxy_async();
+        mbar_arrive(&o_rdy[g]);
     }
-
-    // Full forward for the env owned by this thread; obs = float32 observation (S values).  All 128 env threads of
-    // the CTA call this together.  Returns net(obs) (pre-tanh, pre-prior).
-    __device__ __forceinline__ float forward(int row, const float *obs) {
-        constexpr int Hh = G::Hh;
-        write_obs(row, obs);
-        signal_a();
-        if constexpr (G::kModular) {
-            wait_d();                               // P0: D[0:H] = other_net.0 pre-activation (net_residual.py:151)
-            epilogue_to_a<H>(row, 0, 0);
-            signal_a();
-            wait_d();                               // P1: D[0:H/2] = other_net.2 (:152), D[H/2:H] = integrator_net.0 units [0,H/2) (:154)
-            epilogue_to_a<Hh>(row, Hh, 0);
-            signal_a();
-            wait_d();                               // P2: D[H/2:H] = integrator_net.0 units [H/2,H)
-            epilogue_to_a<Hh>(row, Hh, Hh);
-            signal_a();
-            wait_d();                               // P3: D[H/2:H] = integrator_net.2 (:155)
-            epilogue_to_a<H>(row, 0, 0);            // cat(tanh(other), tanh(integrator)) (:170)
-            signal_a();
-            wait_d();                               // P4: D[0:H] = net.0 (:157)
-            epilogue_to_a<H>(row, 0, 0);
-            signal_a();
-            wait_d();                               // P5: D[:, 0] = net.2 (:158)
-        } else {
-            wait_d();
-            epilogue_to_a<H>(row, 0, 0);
-            signal_a();
-            wait_d();
-            epilogue_to_a<H>(row, 0, 0);
-            signal_a();
-            wait_d();
-            epilogue_to_a<H>(row, 0, 0);
-            signal_a();
-            wait_d();
-        }
-        const float out = tmem_ld1(tmem_base + ((uint32_t)((row / 32) * 32) << 16));
-        tc_fence_before();  // orders this read before the next step's MMAs (they follow the a_ready arrive)
+    // net(obs) of pass q for this row (pre-tanh, pre-prior); releases the output column for the next pass
+    __device__ __forceinline__ float read_out(int row, int q) {
+        mbar_wait(out_rdy, (uint32_t)q & 1u);
+        tc_fence_after();
+        const float out = tmem_ld1(tmem_base + ((uint32_t)((row / 32) * 32) << 16) + (uint32_t)G::OutCol);
+        tc_fence_before();
+        mbar_arrive(out_read);
         return out;
     }
 };
