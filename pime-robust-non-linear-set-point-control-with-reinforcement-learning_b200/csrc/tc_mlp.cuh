@@ -40,28 +40,24 @@ constexpr int kWorkerThreads = 256;
 constexpr int kOwnerThreads = 128;
 constexpr int kThreads = 448;           // 8 worker warps + 4 owner warps + MMA warp + TMA warp
 constexpr int kMmaWarp = 12, kTmaWarp = 13;
-constexpr int kMaxStages = 16;
-constexpr int kMaxBlkBytes = 8192;
+constexpr int kMaxStages = 8;
+constexpr int kMaxBlkBytes = 16384;
 constexpr int kChunkBytes = kRows * 16;    // one K core-matrix column (8 fp16) for all 128 rows = 2048 B
 constexpr int kK16Bytes = 2 * kChunkBytes; // one K=16 slice of an A operand = 4096 B
-constexpr int kMaxBlocks = 56;
-constexpr int kHeaderBytes = 1024;         // the block program at the head of the pack (kMaxBlocks x 16 B)
+constexpr int kMaxBlocks = 32;
+constexpr int kHeaderBytes = 512;          // the block list at the head of the pack (kMaxBlocks x 16 B)
 constexpr int kMaxKP = 64;                 // widest first-layer operand (2 x 31 inputs + 2)
-constexpr int kMaxChunks = 8;              // 32-column chunks of a layer (H <= 256)
+constexpr int kMaxChunks = 4;              // 64-column chunks of a layer (H <= 256): the granularity of the MMA pipelining
 
 // ------------------------------------------------------------------------------------------------ block program
 enum : uint32_t {
     BLK_FRESH = 1u,       // first MMA of the block overwrites the accumulator
-    BLK_WAIT_OBS = 2u,    // first block of a pass: wait for the group's observation operand (and the previous output read)
-    BLK_COMMIT_D = 4u,    // tcgen05.commit -> d_ready after the block (a TMEM buffer is complete)
-    BLK_PHASE_END = 8u,   // forget which chunk barriers were waited on
-    BLK_FREE = 16u,       // tcgen05.commit -> a_free[chunk] after the block (the A chunk may be overwritten)
-    BLK_OBS_A = 32u,      // A operand is the observation operand of the current group
-    BLK_OUT = 64u         // tcgen05.commit -> out_rdy (net(obs) is in TMEM)
+    BLK_OBS_A = 32u       // A operand is the observation operand of the current group
 };
-// flags bits 8..15: chunk barriers a_rdy[j] to wait on before the block; bits 16..18: chunk index for BLK_FREE
+// The list is what the TMA producer streams, in order; the MMA warp runs the same order as a static program
+// (Engine::mma_loop), the flags / operand fields document each block and are checked by the host-side tests.
 
-struct Blk {             // one streamed weight block = k16s MMAs of shape 128 x (8*nb8) x 16
+struct Blk {             // one streamed weight block (<= 16 KB) = k16s MMAs of shape 128 x (8*nb8) x 16
     uint32_t src_off;    // byte offset inside the fp16 section of the pack
     uint16_t bytes16;    // block bytes / 16
     uint8_t nb8;         // N / 8
@@ -100,46 +96,35 @@ struct PackLayout {
 };
 
 struct GemmSpec {
-    int type, N, n_real, n0, K16, a_off, d_col, w_off, ld, b_off, c0, cN;
+    int type, N, n_real, K16, a_off, d_col, w_off, ld, b_off, c0, cN;
     uint32_t flags;        // extra flags for every block
-    uint32_t first_wait;   // chunk mask the first block waits on (accumulator aliasing lag)
 };
 
+__host__ __device__ constexpr int blk_k16(int N, int K16) {   // K=16 slices per block: as many as fit 16 KB
+    return kMaxBlkBytes / (N * 32) < K16 ? kMaxBlkBytes / (N * 32) : K16;
+}
+
 inline bool emit_gemm(PackLayout &L, const GemmSpec &g) {
-    const int NB = g.N < 128 ? g.N : 128, nbn = g.N / NB;
-    int kpb = kMaxBlkBytes / (NB * 32);
-    if (g.type == SRC_HID && kpb > 2) kpb = 2;   // hidden layers: one block per 32-column chunk of the A operand
-    if (kpb < 1) kpb = 1;
-    if (kpb > g.K16) kpb = g.K16;
-    bool first = true;
+    const int kpb = blk_k16(g.N, g.K16);
+    if (g.N > 256 || g.N % 16 || kpb < 1) return false;
     for (int k = 0; k < g.K16; k += kpb) {
         const int kk = g.K16 - k < kpb ? g.K16 - k : kpb;
-        for (int nb = 0; nb < nbn; ++nb) {
-            if (L.nblk >= kMaxBlocks) return false;
-            Blk &b = L.blk[L.nblk];
-            BlkSrc &s = L.bsrc[L.nblk];
-            b.src_off = (uint32_t)L.f16_bytes;
-            b.bytes16 = (uint16_t)(NB * kk * 32 / 16);
-            b.nb8 = (uint8_t)(NB / 8);
-            b.k16s = (uint8_t)kk;
-            b.a_off16 = (uint16_t)((g.a_off + k * kK16Bytes) / 16);
-            b.d_col = (uint16_t)(g.d_col + nb * NB);
-            b.flags = g.flags | (k == 0 && g.type != SRC_HID ? BLK_FRESH : 0u);
-            if (first) b.flags |= g.first_wait << 8;
-            if (g.type == SRC_HID) {
-                const int chunk = k / 2;                       // K=32 per chunk
-                b.flags |= (1u << chunk) << 8;
-                if (kk > 2) return false;
-                if ((g.flags & BLK_FREE) && nb == nbn - 1) b.flags |= (uint32_t)chunk << 16; else b.flags &= ~BLK_FREE;
-            }
-            s.type = g.type; s.w_off = g.w_off; s.ld = g.ld; s.b_off = g.b_off;
-            s.n0 = g.n0 + nb * NB;
-            s.n_real = g.n_real - nb * NB;
-            s.k0 = k * 16; s.c0 = g.c0; s.cN = g.cN;
-            L.f16_bytes += NB * kk * 32;
-            ++L.nblk;
-            first = false;
-        }
+        if (L.nblk >= kMaxBlocks) return false;
+        Blk &b = L.blk[L.nblk];
+        BlkSrc &s = L.bsrc[L.nblk];
+        b.src_off = (uint32_t)L.f16_bytes;
+        b.bytes16 = (uint16_t)(g.N * kk * 32 / 16);
+        b.nb8 = (uint8_t)(g.N / 8);
+        b.k16s = (uint8_t)kk;
+        b.a_off16 = (uint16_t)((g.a_off + k * kK16Bytes) / 16);
+        b.d_col = (uint16_t)g.d_col;
+        b.flags = g.flags | (k == 0 && g.type != SRC_HID ? BLK_FRESH : 0u);
+        s.type = g.type; s.w_off = g.w_off; s.ld = g.ld; s.b_off = g.b_off;
+        s.n0 = 0;
+        s.n_real = g.n_real;
+        s.k0 = k * 16; s.c0 = g.c0; s.cN = g.cN;
+        L.f16_bytes += g.N * kk * 32;
+        ++L.nblk;
     }
     return true;
 }
@@ -155,15 +140,14 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
     const int a_obs = geo_obs_off(H), a_ones = geo_ones_off(c.kind, H);
     const int Da = 0, Db = H;
     bool ok = true;
-    auto end = [&](uint32_t f) { L.blk[L.nblk - 1].flags |= f | BLK_PHASE_END; };
-    auto bias = [&](int N, int n_real, int b_off, int d_col, uint32_t first_wait) {
-        ok = ok && emit_gemm(L, GemmSpec{SRC_BIAS, N, n_real, 0, 1, a_ones, d_col, 0, 0, b_off, 0, 0, 0u, first_wait});
+    auto bias = [&](int N, int n_real, int b_off, int d_col) {
+        ok = ok && emit_gemm(L, GemmSpec{SRC_BIAS, N, n_real, 1, a_ones, d_col, 0, 0, b_off, 0, 0, 0u});
     };
-    auto hid = [&](int N, int n_real, int w_off, int d_col, uint32_t flags) {   // accumulates on top of the bias block
-        ok = ok && emit_gemm(L, GemmSpec{SRC_HID, N, n_real, 0, HK, 0, d_col, w_off, H, 0, 0, 0, flags, 0u});
+    auto hid = [&](int N, int n_real, int w_off, int d_col) {   // accumulates on top of the bias block
+        ok = ok && emit_gemm(L, GemmSpec{SRC_HID, N, n_real, HK, 0, d_col, w_off, H, 0, 0, 0, 0u});
     };
     auto l1 = [&](int N, int w_off, int ld, int b_off, int c0, int cN, int d_col) {
-        ok = ok && emit_gemm(L, GemmSpec{SRC_L1, N, N, 0, L.KP / 16, a_obs, d_col, w_off, ld, b_off, c0, cN, BLK_OBS_A, 0u});
+        ok = ok && emit_gemm(L, GemmSpec{SRC_L1, N, N, L.KP / 16, a_obs, d_col, w_off, ld, b_off, c0, cN, BLK_OBS_A});
     };
     if (c.kind == PIME_ACTOR_MODULAR) {
         const int So = S - D;
@@ -175,13 +159,12 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
         for (int j = 0; j < 12; ++j) { L.src[j] = o; o += sizes[j]; }
         L.param_count = o;
         L.nin = 4; L.nterms = 3; L.KP = 16;   // inputs (o0,o1,o2,I): 3 x 4 + 2 = 14 <= 16
-        const uint32_t lag = (1u << ((Hh + 31) / 32)) - 1u;   // chunks of Da that must be consumed before Da[0:H/2] is reused
-        l1(H, L.src[0], So, L.src[1], 0, So, Da);                                       // P0 other_net.0 -> Da
-        l1(H, L.src[4], 1, L.src[5], 3, 1, Db);                      end(BLK_COMMIT_D);  //    integrator_net.0 -> Db
-        bias(Hh, Hh, L.src[3], Da, lag); hid(Hh, Hh, L.src[2], Da, BLK_FREE);  end(0);   // P1 other_net.2 -> Da[0:H/2]
-        bias(Hh, Hh, L.src[7], Da + Hh, 0); hid(Hh, Hh, L.src[6], Da + Hh, 0); end(BLK_COMMIT_D);  // P2 integrator_net.2
-        bias(H, H, L.src[9], Db, 0); hid(H, H, L.src[8], Db, 0);     end(BLK_COMMIT_D);  // P3 net.0 -> Db
-        bias(16, 1, L.src[11], Da, 0); hid(16, 1, L.src[10], Da, 0); end(BLK_COMMIT_D | BLK_OUT);  // P4 net.2 -> Da[0:16]
+        l1(H, L.src[0], So, L.src[1], 0, So, Da);                          // P0 other_net.0 -> Da
+        l1(H, L.src[4], 1, L.src[5], 3, 1, Db);                            //    integrator_net.0 -> Db
+        bias(Hh, Hh, L.src[3], Da); hid(Hh, Hh, L.src[2], Da);             // P1 other_net.2 -> Da[0:H/2]
+        bias(Hh, Hh, L.src[7], Da + Hh); hid(Hh, Hh, L.src[6], Da + Hh);   // P2 integrator_net.2 -> Da[H/2:H]
+        bias(H, H, L.src[9], Db); hid(H, H, L.src[8], Db);                 // P3 net.0 -> Db
+        bias(16, 1, L.src[11], Da); hid(16, 1, L.src[10], Da);             // P4 net.2 -> Da[0:16]
     } else {
         // state_dict order: net.0.{w,b} net.2.{w,b} net.4.{w,b} net.6.{w,b}
         const int sizes[8] = {H * S, H, H * H, H, H * H, H, H, 1};
@@ -192,13 +175,12 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
         L.nterms = 3 * S + 2 <= 32 ? 3 : 2;
         L.KP = ((L.nterms * S + 2 + 15) / 16) * 16;
         if (L.KP > kMaxKP) return false;
-        l1(H, L.src[0], S, L.src[1], 0, S, Da);                      end(BLK_COMMIT_D);  // P0 net.0 -> Da
-        bias(H, H, L.src[3], Db, 0); hid(H, H, L.src[2], Db, 0);     end(BLK_COMMIT_D);  // P1 net.2 -> Db
-        bias(H, H, L.src[5], Da, 0); hid(H, H, L.src[4], Da, 0);     end(BLK_COMMIT_D);  // P2 net.4 -> Da
-        bias(16, 1, L.src[7], Db, 0); hid(16, 1, L.src[6], Db, 0);   end(BLK_COMMIT_D | BLK_OUT);  // P3 net.6 -> Db[0:16]
+        l1(H, L.src[0], S, L.src[1], 0, S, Da);                            // P0 net.0 -> Da
+        bias(H, H, L.src[3], Db); hid(H, H, L.src[2], Db);                 // P1 net.2 -> Db
+        bias(H, H, L.src[5], Da); hid(H, H, L.src[4], Da);                 // P2 net.4 -> Da
+        bias(16, 1, L.src[7], Db); hid(16, 1, L.src[6], Db);               // P3 net.6 -> Db[0:16]
     }
     if (!ok) return false;
-    L.blk[0].flags |= BLK_WAIT_OBS;
     L.total_bytes = kHeaderBytes + L.f16_bytes;
     return true;
 }
@@ -219,13 +201,15 @@ inline MlpParams make_mlp_params(const PackLayout &L, const void *pack) {
 template <int KIND, int H> struct Geo {
     static constexpr bool kModular = KIND == PIME_ACTOR_MODULAR;
     static constexpr bool kRelu = KIND == PIME_CRITIC_ADV;
-    static constexpr int NCh = H / 32 < 1 ? 1 : H / 32;      // 32-column chunks per layer
+    static constexpr int NP = H / 32;                        // 32-column pieces per layer (one worker epilogue step)
+    static constexpr int NCh = (H + 63) / 64;                // 64-column chunks per layer (MMA pipelining granularity)
+    static constexpr int ChunkArrivals = H >= 64 ? 2 * kRows : kRows;  // both halves write a piece of every chunk
     static constexpr int ABytes = geo_abytes(H);
     static constexpr int ObsOff = geo_obs_off(H);
     static constexpr int ObsGroupBytes = geo_obs_group_bytes(KIND);
     static constexpr int OnesOff = geo_ones_off(KIND, H);
     static constexpr int RingOff = OnesOff + kK16Bytes;
-    static constexpr int Stages = kModular ? 16 : 13;
+    static constexpr int Stages = kModular ? 8 : 7;
     static constexpr int TblOff = RingOff + Stages * kMaxBlkBytes;
     static constexpr int BarOff = TblOff + kMaxBlocks * 16;
     static constexpr int SmemBytes = BarOff + 512;
@@ -405,7 +389,7 @@ template <int KIND, int H> struct Engine {
         const int tid = threadIdx.x;
         if (tid == 0) {
             for (int s = 0; s < G::Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-            for (int j = 0; j < kMaxChunks; ++j) { mbar_init(&a_rdy[j], kRows); mbar_init(&a_free[j], 1); }
+            for (int j = 0; j < kMaxChunks; ++j) { mbar_init(&a_rdy[j], G::ChunkArrivals); mbar_init(&a_free[j], 1); }
             mbar_init(&o_rdy[0], kOwnerThreads);
             mbar_init(&o_rdy[1], kOwnerThreads);
             mbar_init(d_ready, 1);
@@ -458,12 +442,14 @@ template <int KIND, int H> struct Engine {
     uint64_t adesc_base;     // descriptor of the operand area start (A tile, observation and ones operands share LBO/SBO)
 
     template <int N, bool FRESH>
-    __device__ __forceinline__ void blk(uint32_t a_off, int k16s, uint32_t d_col, uint64_t *x1 = nullptr, uint64_t *x2 = nullptr) {
+    __device__ __forceinline__ void blk(uint32_t a_off, int k16s, uint32_t d_col, uint64_t *x1 = nullptr, uint64_t *x2 = nullptr,
+                                        uint64_t *x3 = nullptr) {
         mbar_wait(&full[m_st], m_ph);
         tc_fence_after();
         if (elect_one()) {
             const uint32_t b_addr = smem_u32(sRing) + m_st * kMaxBlkBytes;
             constexpr uint32_t idesc = make_idesc(kRows, N);
+#pragma unroll 4
             for (int kk = 0; kk < k16s; ++kk) {
                 const uint64_t adesc = adesc_base + (uint64_t)((a_off + (uint32_t)kk * kK16Bytes) >> 4);
                 const uint64_t bdesc = make_desc(b_addr + (uint32_t)kk * 2u * (N * 16), N * 16, 128);
@@ -472,17 +458,53 @@ template <int KIND, int H> struct Engine {
             mma_commit(&empty[m_st]);  // frees the ring slot once these MMAs have read it
             if (x1) mma_commit(x1);
             if (x2) mma_commit(x2);
+            if (x3) mma_commit(x3);
         }
         __syncwarp();
         if (++m_st == (uint32_t)G::Stages) { m_st = 0; m_ph ^= 1; }
     }
 
+    // One hidden layer: bias block (waits for the first `lag` chunks when the accumulator aliases columns that the
+    // feeding epilogue is still reading), then the weight blocks, each as soon as the A chunks it reads are written.
+    // FREE: release each A chunk (a_free) as soon as its last reader is issued.  e1/e2: barriers committed with the last block.
+    template <int N, bool FREE>
+    __device__ __forceinline__ void layer(uint32_t d_col, uint32_t apar, int lag, uint64_t *e1, uint64_t *e2) {
+        constexpr int K16 = H / 16, kpb = blk_k16(N, K16);
+        int waited = 0;
+        auto need = [&](int upto) {   // chunks [0, upto) of the feeding epilogue are in shared memory
+            if (waited < upto) {
+                for (; waited < upto; ++waited) mbar_wait(&a_rdy[waited], apar);
+                tc_fence_after();
+            }
+        };
+        need(lag);
+        blk<N, true>((uint32_t)G::OnesOff, 1, d_col);
+#pragma unroll
+        for (int k = 0; k < K16; k += kpb) {
+            const int c_hi = ((k + kpb) * 16 + 63) / 64;   // chunks touched by K columns [16k, 16(k+kpb))
+            need(c_hi);
+            const bool last = k + kpb >= K16;
+            uint64_t *f1 = nullptr, *f2 = nullptr;
+            if (FREE) {   // chunks completed by this block (kpb*16 is 32, 64 or a multiple of 64)
+                const int c_done_lo = (k * 16) / 64, c_done_hi = last ? G::NCh : ((k + kpb) * 16) / 64;
+                if (c_done_hi > c_done_lo) f1 = &a_free[c_done_lo];
+                if (c_done_hi > c_done_lo + 1) f2 = &a_free[c_done_lo + 1];
+                if (c_done_hi > c_done_lo + 2) {   // a block spanning 3+ chunks: commit the rest separately
+                    if (elect_one()) for (int c = c_done_lo + 2; c < c_done_hi; ++c) mma_commit(&a_free[c]);
+                    __syncwarp();
+                }
+            }
+            if (FREE) blk<N, false>((uint32_t)k * kK16Bytes, kpb, d_col, f1, f2, last ? e1 : nullptr);
+            else blk<N, false>((uint32_t)k * kK16Bytes, kpb, d_col, last ? e1 : nullptr, last ? e2 : nullptr);
+        }
+    }
+
     __device__ __forceinline__ void mma_loop(int passes) {
-        constexpr int NB = H < 128 ? H : 128, nbn = H / NB, Hh = H / 2, NCh = G::NCh;
-        constexpr uint32_t Da = 0, Db = H, ones = G::OnesOff;
+        constexpr int Hh = H / 2;
+        constexpr uint32_t Da = 0, Db = H;
         m_st = 0; m_ph = 0;
         adesc_base = make_desc(smem_u32(sA), kChunkBytes, 128);
-        uint32_t apar = 0;   // parity of the next completion of the chunk barriers (all chunks complete once per epilogue)
+        uint32_t apar = 0;   // parity of the next completion of the chunk barriers (every chunk completes once per epilogue)
         for (int q = 0; q < passes; ++q) {
             const uint32_t g = (uint32_t)q & 1u;
             const uint32_t obs = (uint32_t)G::ObsOff + g * (uint32_t)G::ObsGroupBytes;
@@ -490,91 +512,30 @@ template <int KIND, int H> struct Engine {
             if (q > 0) mbar_wait(out_read, ((uint32_t)q - 1u) & 1u);   // the previous pass's output column has been read
             tc_fence_after();
             if constexpr (G::kModular) {
-                constexpr int lag = (Hh + 31) / 32;   // chunks of Da to be consumed before Da[0:H/2] is overwritten
-                // P0: other_net.0 -> Da, integrator_net.0 -> Db
-#pragma unroll
-                for (int nb = 0; nb < nbn; ++nb) blk<NB, true>(obs, 1, Da + nb * NB);
-#pragma unroll
-                for (int nb = 0; nb < nbn; ++nb) blk<NB, true>(obs, 1, Db + nb * NB, nb == nbn - 1 ? d_ready : nullptr);
-                // P1: other_net.2 -> Da[0:H/2], behind the epilogue of Da
-#pragma unroll
-                for (int j = 0; j < lag; ++j) mbar_wait(&a_rdy[j], apar);
-                tc_fence_after();
-                blk<Hh, true>(ones, 1, Da);
-#pragma unroll
-                for (int j = 0; j < NCh; ++j) {
-                    if (j >= lag) { mbar_wait(&a_rdy[j], apar); tc_fence_after(); }
-                    blk<Hh, false>(j * 2 * kK16Bytes, 2, Da, &a_free[j]);
-                }
+                blk<H, true>(obs, 1, Da);                              // P0: other_net.0 -> Da
+                blk<H, true>(obs, 1, Db, d_ready);                     //     integrator_net.0 -> Db
+                layer<Hh, true>(Da, apar, (Hh + 63) / 64, nullptr, nullptr);   // P1: other_net.2 -> Da[0:H/2], behind the epilogue of Da
                 apar ^= 1;
-                // P2: integrator_net.2 -> Da[H/2:H], behind the epilogue of Db
-                blk<Hh, true>(ones, 1, Da + Hh);
-#pragma unroll
-                for (int j = 0; j < NCh; ++j) {
-                    mbar_wait(&a_rdy[j], apar);
-                    tc_fence_after();
-                    blk<Hh, false>(j * 2 * kK16Bytes, 2, Da + Hh, j == NCh - 1 ? d_ready : nullptr);
-                }
+                layer<Hh, false>(Da + Hh, apar, 0, d_ready, nullptr);  // P2: integrator_net.2 -> Da[H/2:H], behind the epilogue of Db
                 apar ^= 1;
-                // P3: net.0 on cat -> Db
-#pragma unroll
-                for (int nb = 0; nb < nbn; ++nb) blk<NB, true>(ones, 1, Db + nb * NB);
-#pragma unroll
-                for (int j = 0; j < NCh; ++j) {
-                    mbar_wait(&a_rdy[j], apar);
-                    tc_fence_after();
-#pragma unroll
-                    for (int nb = 0; nb < nbn; ++nb)
-                        blk<NB, false>(j * 2 * kK16Bytes, 2, Db + nb * NB, (j == NCh - 1 && nb == nbn - 1) ? d_ready : nullptr);
-                }
+                layer<H, false>(Db, apar, 0, d_ready, nullptr);        // P3: net.0 on cat -> Db
                 apar ^= 1;
-                // P4: net.2 -> Da[0:16]
-                blk<16, true>(ones, 1, Da);
-#pragma unroll
-                for (int j = 0; j < NCh; ++j) {
-                    mbar_wait(&a_rdy[j], apar);
-                    tc_fence_after();
-                    blk<16, false>(j * 2 * kK16Bytes, 2, Da, j == NCh - 1 ? d_ready : nullptr, j == NCh - 1 ? out_rdy : nullptr);
-                }
+                layer<16, false>(Da, apar, 0, d_ready, out_rdy);       // P4: net.2 -> Da[0:16]
                 apar ^= 1;
             } else {
-                // P0: net.0 -> Da (first-layer operand K = KP)
-                const int K16 = mp.KP / 16;
-                constexpr int kpb = kMaxBlkBytes / (NB * 32);
+                const int K16 = mp.KP / 16;                            // P0: net.0 -> Da (first-layer operand K = KP)
+                constexpr int kpb = blk_k16(H, 4);
                 for (int k = 0; k < K16; k += kpb) {
                     const int kk = K16 - k < kpb ? K16 - k : kpb;
-                    const bool last_k = k + kpb >= K16;
-#pragma unroll
-                    for (int nb = 0; nb < nbn; ++nb) {
-                        uint64_t *x = (last_k && nb == nbn - 1) ? d_ready : nullptr;
-                        if (k == 0) blk<NB, true>(obs, kk, Da + nb * NB, x);
-                        else blk<NB, false>(obs + (uint32_t)k * kK16Bytes, kk, Da + nb * NB, x);
-                    }
+                    uint64_t *x = k + kpb >= K16 ? d_ready : nullptr;
+                    if (k == 0) blk<H, true>(obs, kk, Da, x);
+                    else blk<H, false>(obs + (uint32_t)k * kK16Bytes, kk, Da, x);
                 }
-                // P1: net.2 -> Db;  P2: net.4 -> Da
-#pragma unroll
-                for (int p = 0; p < 2; ++p) {
-                    const uint32_t d = p == 0 ? Db : Da;
-#pragma unroll
-                    for (int nb = 0; nb < nbn; ++nb) blk<NB, true>(ones, 1, d + nb * NB);
-#pragma unroll
-                    for (int j = 0; j < NCh; ++j) {
-                        mbar_wait(&a_rdy[j], apar);
-                        tc_fence_after();
-#pragma unroll
-                        for (int nb = 0; nb < nbn; ++nb)
-                            blk<NB, false>(j * 2 * kK16Bytes, 2, d + nb * NB, (j == NCh - 1 && nb == nbn - 1) ? d_ready : nullptr);
-                    }
-                    apar ^= 1;
-                }
-                // P3: net.6 -> Db[0:16]
-                blk<16, true>(ones, 1, Db);
-#pragma unroll
-                for (int j = 0; j < NCh; ++j) {
-                    mbar_wait(&a_rdy[j], apar);
-                    tc_fence_after();
-                    blk<16, false>(j * 2 * kK16Bytes, 2, Db, j == NCh - 1 ? d_ready : nullptr, j == NCh - 1 ? out_rdy : nullptr);
-                }
+                layer<H, false>(Db, apar, 0, d_ready, nullptr);        // P1: net.2 -> Db
+                apar ^= 1;
+                layer<H, false>(Da, apar, 0, d_ready, nullptr);        // P2: net.4 -> Da
+                apar ^= 1;
+                layer<16, false>(Db, apar, 0, d_ready, out_rdy);       // P3: net.6 -> Db[0:16]
                 apar ^= 1;
             }
         }
@@ -584,30 +545,30 @@ template <int KIND, int H> struct Engine {
     __device__ __forceinline__ void a_store8(int row, int kchunk, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3) {
         *reinterpret_cast<uint4 *>(sA + (size_t)kchunk * kChunkBytes + row * 16) = make_uint4(p0, p1, p2, p3);
     }
-    // A[:, 32j .. 32j+32) = act(D[:, dcol + 32j ..)) for the chunks j of this half; the bias is already in D.
-    // WAIT_FREE: the previous reader of A chunk j is still in flight (no d_ready wait in between): wait a_free[j].
+    // A[:, 32j .. 32j+32) = act(D[:, dcol + 32j ..)) for the 32-column pieces j of this half (even / odd); the bias
+    // is already in D.  Piece j belongs to chunk j/2, whose barrier collects both halves.
+    // WAIT_FREE: the previous reader of the A chunk may still be in flight (no d_ready wait in between): wait a_free.
     template <bool WAIT_FREE> __device__ __forceinline__ void epilogue(int row, int half, int dcol, uint32_t free_parity) {
         const uint32_t taddr = tmem_base + ((uint32_t)((row / 32) * 32) << 16) + (uint32_t)dcol;
-        constexpr int W = H < 32 ? H : 32;   // chunk width
         float v[2][32];
-        if (half < G::NCh) tmem_ld32_issue(taddr + half * 32, v[0]);
+        if (half < G::NP) tmem_ld32_issue(taddr + half * 32, v[0]);
 #pragma unroll
-        for (int it = 0; it < (G::NCh + 1) / 2; ++it) {
+        for (int it = 0; it < (G::NP + 1) / 2; ++it) {
             const int j = half + 2 * it;
-            if (j < G::NCh) {
+            if (j < G::NP) {
                 tmem_wait_ld();
-                if (j + 2 < G::NCh) tmem_ld32_issue(taddr + (j + 2) * 32, v[(it + 1) & 1]);
+                if (j + 2 < G::NP) tmem_ld32_issue(taddr + (j + 2) * 32, v[(it + 1) & 1]);
                 float(&x)[32] = v[it & 1];
 #pragma unroll
-                for (int e = 0; e < W; ++e) x[e] = act_fn<G::kRelu>(x[e]);
-                if (WAIT_FREE) mbar_wait(&a_free[j], free_parity);
+                for (int e = 0; e < 32; ++e) x[e] = act_fn<G::kRelu>(x[e]);
+                if (WAIT_FREE) mbar_wait(&a_free[j >> 1], free_parity);
 #pragma unroll
-                for (int qd = 0; qd < W / 8; ++qd)
+                for (int qd = 0; qd < 4; ++qd)
                     a_store8(row, j * 4 + qd, pack_h2(x[qd * 8 + 0], x[qd * 8 + 1]), pack_h2(x[qd * 8 + 2], x[qd * 8 + 3]),
                              pack_h2(x[qd * 8 + 4], x[qd * 8 + 5]), pack_h2(x[qd * 8 + 6], x[qd * 8 + 7]));
                 tc_fence_before();
                 fence_proxy_async();
-                mbar_arrive(&a_rdy[j]);
+                mbar_arrive(&a_rdy[j >> 1]);
             }
         }
     }
