@@ -8,6 +8,12 @@ namespace pime {
 __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ tc::PackLayout L, const float *__restrict__ p,
                                                    uint8_t *__restrict__ out) {
     const int b = blockIdx.x;
+    if (b == L.nblk) {   // fp32 output layer: weight vector + bias into the header
+        float *ow = reinterpret_cast<float *>(out + tc::kOutWOff);
+        for (int j = threadIdx.x; j < L.H; j += blockDim.x) ow[j] = p[L.out_w + j];
+        if (threadIdx.x == 0) ow[L.H] = p[L.out_b];
+        return;
+    }
     const tc::Blk B = L.blk[b];
     const tc::BlkSrc s = L.bsrc[b];
     if (threadIdx.x == 0) reinterpret_cast<tc::Blk *>(out)[b] = B;
@@ -122,7 +128,7 @@ int pime_actor_pack(const pime_actor_config *cfg, const float *params, void *pac
     PIME_REQUIRE(tc::make_pack_layout(*cfg, L), "unsupported actor dimensions (H in {32,64,128,256}, S <= 32, modular: S-1 <= 3)");
     PIME_REQUIRE(((uintptr_t)pack & 127) == 0, "pack must be 128-byte aligned");
     if (int rc = require_device()) return rc;
-    pack_kernel<<<L.nblk, 256, 0, (cudaStream_t)stream>>>(L, params, (uint8_t *)pack);
+    pack_kernel<<<L.nblk + 1, 256, 0, (cudaStream_t)stream>>>(L, params, (uint8_t *)pack);
     PIME_LAUNCH_CHECK();
     return PIME_OK;
 }

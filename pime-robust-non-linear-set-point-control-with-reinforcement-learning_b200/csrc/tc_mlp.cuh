@@ -20,13 +20,14 @@
 //     relative: an fp32-grade first layer; 2 terms when 3S+2 > 32);
 //   * hidden layers: A = fp16 activations written by the previous epilogue, B = fp16 weights; the bias enters
 //     through one extra K=16 MMA against a constant "ones" operand, B = [b_hi b_lo 0 ...];
-//   * output layer Linear(H -> 1): N=16 MMAs whose row 0 is the weight vector; one TMEM column is net(obs).
+//   * output layer Linear(H -> 1): an fp32 dot product inside the last epilogue (FMA pipe, idle otherwise); the two
+//     column halves of a row meet in shared memory, where the row's owner picks net(obs) up.
 //
 // Layers (reference elegantrl/net_residual.py), Da = TMEM columns [0,H), Db = [H,2H):
 //   modular (:138-205): P0 other_net.0 -> Da, integrator_net.0 -> Db;  P1 other_net.2 -> Da[0:H/2] (behind the epilogue
 //                       of Da);  P2 integrator_net.2 -> Da[H/2:H] (behind the epilogue of Db);  P3 net.0 on
-//                       cat = Da -> Db;  P4 net.2 -> Da[0:16].
-//   plain (:6-66) / CriticAdv (net.py:274-277): P0 net.0 -> Da, P1 net.2 -> Db, P2 net.4 -> Da, P3 net.6 -> Db[0:16].
+//                       cat = Da -> Db;  net.2 in the epilogue of Db.
+//   plain (:6-66) / CriticAdv (net.py:274-277): P0 net.0 -> Da, P1 net.2 -> Db, P2 net.4 -> Da, net.6 in the epilogue of Da.
 #pragma once
 
 #include "pime_common.cuh"
@@ -45,7 +46,8 @@ constexpr int kMaxBlkBytes = 16384;
 constexpr int kChunkBytes = kRows * 16;    // one K core-matrix column (8 fp16) for all 128 rows = 2048 B
 constexpr int kK16Bytes = 2 * kChunkBytes; // one K=16 slice of an A operand = 4096 B
 constexpr int kMaxBlocks = 32;
-constexpr int kHeaderBytes = 512;          // the block list at the head of the pack (kMaxBlocks x 16 B)
+constexpr int kHeaderBytes = 2048;         // head of the pack: block list (kMaxBlocks x 16 B), then the fp32 output layer
+constexpr int kOutWOff = 512;              // fp32 [H] weight vector + bias of the last Linear(H -> 1), inside the header
 constexpr int kMaxKP = 64;                 // widest first-layer operand (2 x 31 inputs + 2)
 constexpr int kMaxChunks = 4;              // 64-column chunks of a layer (H <= 256): the granularity of the MMA pipelining
 
@@ -91,6 +93,7 @@ struct PackLayout {
     int nblk;
     int f16_bytes, total_bytes;
     int src[12];           // offsets of the state_dict tensors inside `params`
+    int out_w, out_b;      // offsets of the last layer's weight vector / bias inside `params`
     Blk blk[kMaxBlocks];
     BlkSrc bsrc[kMaxBlocks];
 };
@@ -164,7 +167,7 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
         bias(Hh, Hh, L.src[3], Da); hid(Hh, Hh, L.src[2], Da);             // P1 other_net.2 -> Da[0:H/2]
         bias(Hh, Hh, L.src[7], Da + Hh); hid(Hh, Hh, L.src[6], Da + Hh);   // P2 integrator_net.2 -> Da[H/2:H]
         bias(H, H, L.src[9], Db); hid(H, H, L.src[8], Db);                 // P3 net.0 -> Db
-        bias(16, 1, L.src[11], Da); hid(16, 1, L.src[10], Da);             // P4 net.2 -> Da[0:16]
+        L.out_w = L.src[10]; L.out_b = L.src[11];                          // net.2: fp32 dot product inside the last epilogue
     } else {
         // state_dict order: net.0.{w,b} net.2.{w,b} net.4.{w,b} net.6.{w,b}
         const int sizes[8] = {H * S, H, H * H, H, H * H, H, H, 1};
@@ -178,7 +181,7 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
         l1(H, L.src[0], S, L.src[1], 0, S, Da);                            // P0 net.0 -> Da
         bias(H, H, L.src[3], Db); hid(H, H, L.src[2], Db);                 // P1 net.2 -> Db
         bias(H, H, L.src[5], Da); hid(H, H, L.src[4], Da);                 // P2 net.4 -> Da
-        bias(16, 1, L.src[7], Db); hid(16, 1, L.src[6], Db);               // P3 net.6 -> Db[0:16]
+        L.out_w = L.src[6]; L.out_b = L.src[7];                            // net.6: fp32 dot product inside the last epilogue
     }
     if (!ok) return false;
     L.total_bytes = kHeaderBytes + L.f16_bytes;
@@ -211,10 +214,11 @@ template <int KIND, int H> struct Geo {
     static constexpr int RingOff = OnesOff + kK16Bytes;
     static constexpr int Stages = kModular ? 8 : 7;
     static constexpr int TblOff = RingOff + Stages * kMaxBlkBytes;
-    static constexpr int BarOff = TblOff + kMaxBlocks * 16;
+    static constexpr int OutWOff = TblOff + kMaxBlocks * 16;          // fp32 [H] + bias of the output layer
+    static constexpr int PartOff = OutWOff + (H + 4) * 4;              // fp32 [2 groups][2 halves][128 rows] partial dot products
+    static constexpr int BarOff = PartOff + 4 * kRows * 4;
     static constexpr int SmemBytes = BarOff + 512;
     static constexpr int TmemCols = 2 * H < 32 ? 32 : 2 * H;
-    static constexpr int OutCol = kModular ? 0 : H;          // TMEM column of net(obs)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -365,7 +369,8 @@ template <int KIND, int H> struct Engine {
     using G = Geo<KIND, H>;
     uint8_t *sA, *sRing;
     const Blk *tbl;
-    uint64_t *full, *empty, *a_rdy, *a_free, *o_rdy, *d_ready, *out_rdy, *out_read;
+    uint64_t *full, *empty, *a_rdy, *a_free, *o_rdy, *d_ready, *out_rdy;
+    float *sOutW, *sPart;
     uint32_t *tmem_slot;
     uint32_t tmem_base;
     MlpParams mp;
@@ -384,8 +389,9 @@ template <int KIND, int H> struct Engine {
         o_rdy = a_free + kMaxChunks;
         d_ready = o_rdy + 2;
         out_rdy = d_ready + 1;
-        out_read = out_rdy + 1;
-        tmem_slot = reinterpret_cast<uint32_t *>(out_read + 1);
+        tmem_slot = reinterpret_cast<uint32_t *>(out_rdy + 1);
+        sOutW = reinterpret_cast<float *>(smem + G::OutWOff);
+        sPart = reinterpret_cast<float *>(smem + G::PartOff);
         const int tid = threadIdx.x;
         if (tid == 0) {
             for (int s = 0; s < G::Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -393,14 +399,14 @@ template <int KIND, int H> struct Engine {
             mbar_init(&o_rdy[0], kOwnerThreads);
             mbar_init(&o_rdy[1], kOwnerThreads);
             mbar_init(d_ready, 1);
-            mbar_init(out_rdy, 1);
-            mbar_init(out_read, kOwnerThreads);
+            mbar_init(out_rdy, kWorkerThreads);
             fence_barrier_init();
         }
         if (tid / 32 == kMmaWarp) tmem_alloc(tmem_slot, G::TmemCols);
         const uint4 *src = reinterpret_cast<const uint4 *>(mp.pack);
         uint4 *dst = reinterpret_cast<uint4 *>(smem + G::TblOff);
         for (int j = tid; j < mp.nblk; j += kThreads) dst[j] = __ldg(src + j);
+        for (int j = tid; j < H + 1; j += kThreads) sOutW[j] = __ldg(reinterpret_cast<const float *>(mp.pack + kOutWOff) + j);
         // ones operand: K=16 slice whose first two columns are 1.0 (fp16 0x3C00): multiplies [b_hi b_lo 0 ...]
         for (int j = tid; j < 2 * kRows; j += kThreads)
             *reinterpret_cast<uint4 *>(smem + G::OnesOff + j * 16) = j < kRows ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
@@ -509,20 +515,19 @@ template <int KIND, int H> struct Engine {
             const uint32_t g = (uint32_t)q & 1u;
             const uint32_t obs = (uint32_t)G::ObsOff + g * (uint32_t)G::ObsGroupBytes;
             mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);            // the group's observation operand is written
-            if (q > 0) mbar_wait(out_read, ((uint32_t)q - 1u) & 1u);   // the previous pass's output column has been read
             tc_fence_after();
             if constexpr (G::kModular) {
-                blk<H, true>(obs, 1, Da);                              // P0: other_net.0 -> Da
+                blk<H, true>(obs, 1, Da);                              // P0: other_net.0 -> Da (Da was released by the third epilogue)
+                if (q > 0) { mbar_wait(out_rdy, ((uint32_t)q - 1u) & 1u); tc_fence_after(); }   // last epilogue of the previous pass has read Db
                 blk<H, true>(obs, 1, Db, d_ready);                     //     integrator_net.0 -> Db
                 layer<Hh, true>(Da, apar, (Hh + 63) / 64, nullptr, nullptr);   // P1: other_net.2 -> Da[0:H/2], behind the epilogue of Da
                 apar ^= 1;
                 layer<Hh, false>(Da + Hh, apar, 0, d_ready, nullptr);  // P2: integrator_net.2 -> Da[H/2:H], behind the epilogue of Db
                 apar ^= 1;
-                layer<H, false>(Db, apar, 0, d_ready, nullptr);        // P3: net.0 on cat -> Db
-                apar ^= 1;
-                layer<16, false>(Da, apar, 0, d_ready, out_rdy);       // P4: net.2 -> Da[0:16]
+                layer<H, false>(Db, apar, 0, d_ready, nullptr);        // P3: net.0 on cat -> Db; net.2 is the workers' dot product
                 apar ^= 1;
             } else {
+                if (q > 0) { mbar_wait(out_rdy, ((uint32_t)q - 1u) & 1u); tc_fence_after(); }   // last epilogue of the previous pass has read Da
                 const int K16 = mp.KP / 16;                            // P0: net.0 -> Da (first-layer operand K = KP)
                 constexpr int kpb = blk_k16(H, 4);
                 for (int k = 0; k < K16; k += kpb) {
@@ -533,9 +538,7 @@ template <int KIND, int H> struct Engine {
                 }
                 layer<H, false>(Db, apar, 0, d_ready, nullptr);        // P1: net.2 -> Db
                 apar ^= 1;
-                layer<H, false>(Da, apar, 0, d_ready, nullptr);        // P2: net.4 -> Da
-                apar ^= 1;
-                layer<16, false>(Db, apar, 0, d_ready, out_rdy);       // P3: net.6 -> Db[0:16]
+                layer<H, false>(Da, apar, 0, d_ready, nullptr);        // P2: net.4 -> Da; net.6 is the workers' dot product
                 apar ^= 1;
             }
         }
@@ -573,6 +576,36 @@ template <int KIND, int H> struct Engine {
         }
     }
 
+    // Last layer: partial dot product of this half's pieces, sum_c act(D[:, c]) * w_out[c] in fp32; the two halves of
+    // a row meet in sPart[g][half][row], out_rdy collects all 256 workers (and tells the MMA warp that D is free again).
+    __device__ __forceinline__ void epilogue_dot(int row, int half, int dcol, int g) {
+        const uint32_t taddr = tmem_base + ((uint32_t)((row / 32) * 32) << 16) + (uint32_t)dcol;
+        float v[2][32];
+        float acc0 = 0.0f, acc1 = 0.0f;
+        if (half < G::NP) tmem_ld32_issue(taddr + half * 32, v[0]);
+#pragma unroll
+        for (int it = 0; it < (G::NP + 1) / 2; ++it) {
+            const int j = half + 2 * it;
+            if (j < G::NP) {
+                tmem_wait_ld();
+                if (j + 2 < G::NP) tmem_ld32_issue(taddr + (j + 2) * 32, v[(it + 1) & 1]);
+                float(&x)[32] = v[it & 1];
+                const float4 *w = reinterpret_cast<const float4 *>(sOutW + j * 32);
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                    const float4 ww = w[e / 4];
+                    acc0 = fmaf(act_fn<G::kRelu>(x[e + 0]), ww.x, acc0);
+                    acc1 = fmaf(act_fn<G::kRelu>(x[e + 1]), ww.y, acc1);
+                    acc0 = fmaf(act_fn<G::kRelu>(x[e + 2]), ww.z, acc0);
+                    acc1 = fmaf(act_fn<G::kRelu>(x[e + 3]), ww.w, acc1);
+                }
+            }
+        }
+        sPart[(g * 2 + half) * kRows + row] = acc0 + acc1;
+        tc_fence_before();   // the TMEM reads above are ordered before the MMAs that follow out_rdy
+        mbar_arrive(out_rdy);
+    }
+
     __device__ __forceinline__ void worker_loop(int passes) {
         const int tid = threadIdx.x, row = tid & (kRows - 1), half = tid >> 7;
         uint32_t dph = 0;
@@ -589,16 +622,14 @@ template <int KIND, int H> struct Engine {
                 wait_d();                                             // P2: Da = cat pre-activation (:170)
                 epilogue<false>(row, half, 0, 0);                     // feeds net.0 (:157)
                 wait_d();                                             // P3: Db = net.0
-                epilogue<false>(row, half, H, 0);                     // feeds net.2 (:158)
-                wait_d();                                             // P4 (the owners read the output column)
+                epilogue_dot(row, half, H, q & 1);                    // net.2 (:158)
             } else {
                 wait_d();
                 epilogue<false>(row, half, 0, 0);
                 wait_d();
                 epilogue<false>(row, half, H, 0);
                 wait_d();
-                epilogue<false>(row, half, 0, 0);
-                wait_d();
+                epilogue_dot(row, half, 0, q & 1);
             }
         }
     }
@@ -639,14 +670,11 @@ template <int KIND, int H> struct Engine {
         fence_proxy_async();
         mbar_arrive(&o_rdy[g]);
     }
-    // net(obs) of pass q for this row (pre-tanh, pre-prior); releases the output column for the next pass
+    // net(obs) of pass q for this row (pre-tanh, pre-prior): the two half-row partial sums + the output bias
     __device__ __forceinline__ float read_out(int row, int q) {
         mbar_wait(out_rdy, (uint32_t)q & 1u);
-        tc_fence_after();
-        const float out = tmem_ld1(tmem_base + ((uint32_t)((row / 32) * 32) << 16) + (uint32_t)G::OutCol);
-        tc_fence_before();
-        mbar_arrive(out_read);
-        return out;
+        const int g = q & 1;
+        return sPart[(g * 2) * kRows + row] + sPart[(g * 2 + 1) * kRows + row] + sOutW[H];
     }
 };
 
