@@ -346,6 +346,83 @@ def gen_explore(ref, rng, table):
     np.savez_compressed(os.path.join(OUT, "explore.npz"), **out)
 
 
+def gen_ppo(ref, rng):
+    """PPO learner pins (agent.py:611-708): values, old log-probabilities, reward-to-go / GAE / plain advantage, and
+    the losses, gradients and parameters after ONE Adam step of the reference on a fixed index set."""
+    import torch
+
+    out = {}
+    for tag, make, S, H, D in [("modular", lambda: ref.agent_residual.AgentResidualIntegratorModularPPO(), 4, 32, 1),
+                               ("plain", lambda: ref.agent_residual.AgentResidualPPO(), 3, 32, 0)]:
+        torch.manual_seed(77 + S)
+        agent = make()
+        agent.lambda_gae_adv, agent.ratio_clip, agent.lambda_entropy = 0.95, 0.25, 0.02
+        if D:
+            agent.init(H, S, 1, D)
+        else:
+            agent.init(H, S, 1)
+        agent.device = torch.device("cpu")
+        agent.act.to("cpu"); agent.cri.to("cpu")
+        K = rng.uniform(-0.4, 0.4, (S, 1))
+        agent.init_residual({"init_K": K})
+        with torch.no_grad():   # a non-trivial last layer (init_residual zeroes it)
+            agent.act.net[-1].weight.copy_(torch.as_tensor(rng.normal(0, 0.1, (1, H)), dtype=torch.float32))
+            agent.act.net[-1].bias.fill_(0.03)
+        agent.optimizer = torch.optim.Adam([{"params": agent.act.parameters(), "lr": 3e-4}, {"params": agent.cri.parameters(), "lr": 3e-4}])
+        for k, v in _sd_np(agent.act).items():
+            out[f"{tag}.act0.{k}"] = v
+        for k, v in _sd_np(agent.cri).items():
+            out[f"{tag}.cri0.{k}"] = v
+        # synthetic on-policy buffer: n episodes of T steps, episode after episode (the reference's order)
+        n, T, gamma = 6, 20, 0.98
+        L = n * T
+        state = rng.uniform(0, 10, (L, S)).astype(np.float32)
+        state[:, -1] = rng.uniform(-25, 25, L)
+        reward = (-rng.uniform(0, 30, L)).astype(np.float32)
+        mask = np.full(L, gamma, np.float32)
+        mask[T - 1::T] = 0.0
+        noise = rng.standard_normal((L, 1)).astype(np.float32)
+        ts = torch.as_tensor(state)
+        with torch.no_grad():
+            a_avg = agent.act.net(ts) if not D else agent.act.net(torch.cat([agent.act.other_net(ts[:, :S - D]), agent.act.integrator_net(ts[:, S - D:])], -1))
+            action = (a_avg + torch.as_tensor(noise) * agent.act.a_std_log.exp()).numpy()
+            buf_value = agent.cri(ts)
+            buf_logprob = -(torch.as_tensor(noise).pow(2).__mul__(0.5) + agent.act.a_std_log + agent.act.sqrt_2pi_log).sum(1)
+            r_sum, adv_gae = agent.compute_reward_gae(L, torch.as_tensor(reward), torch.as_tensor(mask), buf_value)
+            r_sum2, adv_plain = agent.compute_reward_adv(L, torch.as_tensor(reward), torch.as_tensor(mask), buf_value)
+        out[f"{tag}.state"], out[f"{tag}.reward"], out[f"{tag}.mask"] = state, reward, mask
+        out[f"{tag}.noise"], out[f"{tag}.action"] = noise, action
+        out[f"{tag}.value"], out[f"{tag}.logprob"] = buf_value.numpy()[:, 0], buf_logprob.numpy()
+        out[f"{tag}.r_sum"], out[f"{tag}.adv_gae"], out[f"{tag}.adv_plain"] = r_sum.numpy(), adv_gae.numpy(), adv_plain.numpy()
+        assert np.array_equal(r_sum.numpy(), r_sum2.numpy())
+        # one minibatch of the reference loop (agent.py:632-657) on fixed indices
+        idx = rng.integers(0, L, 48)
+        ti = torch.as_tensor(idx)
+        st, ac, rs, lp, ad = ts[ti], torch.as_tensor(action)[ti], r_sum[ti], buf_logprob[ti], adv_gae[ti]
+        new_logprob = agent.act.compute_logprob(st, ac)
+        ratio = (new_logprob - lp).exp()
+        obj_surrogate = -torch.min(ad * ratio, ad * ratio.clamp(1 - agent.ratio_clip, 1 + agent.ratio_clip)).mean()
+        obj_entropy = (new_logprob.exp() * new_logprob).mean()
+        obj_actor = obj_surrogate + obj_entropy * agent.lambda_entropy
+        value = agent.cri(st).squeeze(1)
+        obj_critic = agent.criterion(value, rs)
+        obj_united = obj_actor + obj_critic / (rs.std() + 1e-5)
+        agent.optimizer.zero_grad()
+        obj_united.backward()
+        out[f"{tag}.idx"] = idx
+        out[f"{tag}.losses"] = np.array([obj_actor.item(), obj_critic.item(), obj_united.item(), obj_entropy.item()])
+        for name, p in list(agent.act.named_parameters()) + [("cri." + k, v) for k, v in agent.cri.named_parameters()]:
+            if p.grad is not None:
+                out[f"{tag}.grad.{name}"] = p.grad.detach().numpy().copy()
+        agent.optimizer.step()
+        for k, v in _sd_np(agent.act).items():
+            out[f"{tag}.act1.{k}"] = v
+        for k, v in _sd_np(agent.cri).items():
+            out[f"{tag}.cri1.{k}"] = v
+        out[f"{tag}.K"] = K
+    np.savez_compressed(os.path.join(OUT, "ppo.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
@@ -356,6 +433,7 @@ def main():
     table = gen_ph(ref, rng)
     gen_actor(ref, rng)
     gen_explore(ref, rng, table)
+    gen_ppo(ref, np.random.default_rng(20261019))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpime_b200.so")
+LIB_PATH = os.environ.get("PIME_B200_LIB") or os.path.join(HERE, "libpime_b200.so")  # override: kernel A/B experiments
 
 OK, EINVAL, ENODEV, ECUDA, ERANGE, ESTATE = 0, -1, -2, -3, -4, -5
 REWARD = {"distance": 0, "square_distance": 1, "sparse": 2}

@@ -108,12 +108,13 @@ class NonLinearWaterTankChangingParamUniformGoal(_DeviceEnv):
                  gamma=0.99, seed=None, r=9.0, N=100, overflow_cost=-10, n_discrete=1, sample_t=0.02, reward_type="distance",
                  controller_type="P", distance_threshold=0.05, linearize_r=9.0, reset_from_last_state=True,
                  P_control_K=np.array([0.0, 0.4]), P_control_L=np.array([-0.4]), P_max_action=10.0, num_stack=0,
-                 num_envs=1, device="cuda"):
+                 num_envs=1, device="cuda", dtype=torch.float64):
         if controller_type != "P":
             raise NotImplementedError("only controller_type='P' (the registered configuration) is implemented")
         if reset_from_last_state:
             raise NotImplementedError("reset_from_last_state=True is not implemented (registered configs use False)")
         self.num_envs = int(num_envs)
+        self._dtype = dtype   # float64 = the reference's arithmetic (default); float32 = the throughput kernels
         self.a1_range, self.a2_range, self.Kp_range = list(a1), list(a2), list(Kp)
         self.A1, self.A2, self.G, self.z1, self.z2 = A1, A2, G, z1, z2
         self.max_step, self.noise_scale, self.gamma = max_step, noise_scale, gamma
@@ -147,11 +148,11 @@ class NonLinearWaterTankChangingParamUniformGoal(_DeviceEnv):
         return kw
 
     def _make_vec(self, seed):
-        self.vec = WaterTankVec(self.num_envs, dtype=torch.float64, device=self._device, obs_mode=self._obs_mode,
+        self.vec = WaterTankVec(self.num_envs, dtype=self._dtype, device=self._device, obs_mode=self._obs_mode,
                                 num_stack=self.num_stack, seed=seed, **self._cfg_kwargs())
 
     def _clone_vec(self):
-        v = WaterTankVec(self.num_envs, dtype=torch.float64, device=self._device, obs_mode=self._obs_mode,
+        v = WaterTankVec(self.num_envs, dtype=self._dtype, device=self._device, obs_mode=self._obs_mode,
                          num_stack=self.num_stack, seed=self.vec.seed, env_offset=self.vec.env_offset, **self._cfg_kwargs())
         for k in ("h1", "h2", "r", "I", "a1", "a2", "Kp", "t", "episode", "ep_return"):
             getattr(v, k).copy_(getattr(self.vec, k))
@@ -280,12 +281,14 @@ class PH1DChangingParamUniformGoalIntegrator(_DeviceEnv):
     def __init__(self, qww_V=(0.005, 0.015), qc_V=(0.0015, 0.0025), kw=1e-14, kchem=5.6e-10, ka=0.5e-5, MNaOH=0.01, MHA=0.005,
                  MNH3=0.01, MHCl=None, r=7.0, n_discrete=200, sample_t=20, reset_from_last_state=False, reward_type="distance",
                  distance_threshold=0.05, P_control_K=np.array([1, 1]), P_control_L=np.array([-0.4]), action_punishment=0.0,
-                 action_change_punishment=0.0, max_episode_steps=200, seed=None, time_limit=None, num_envs=1, device="cuda"):
+                 action_change_punishment=0.0, max_episode_steps=200, seed=None, time_limit=None, num_envs=1, device="cuda",
+                 dtype=torch.float64):
         if reset_from_last_state:
             raise NotImplementedError("reset_from_last_state=True is not implemented (registered configs use False)")
         if action_change_punishment:
             raise NotImplementedError("action_change_punishment != 0 is not implemented (0 at every registered config)")
         self.num_envs = int(num_envs)
+        self._dtype = dtype
         MHCl = np.arange(0.0, 0.2, step=0.00001) if MHCl is None else np.asarray(MHCl, dtype=np.float64)
         step = float(MHCl[1] - MHCl[0])
         if not np.array_equal(MHCl, np.arange(MHCl.shape[0]) * MHCl[1]):
@@ -311,14 +314,14 @@ class PH1DChangingParamUniformGoalIntegrator(_DeviceEnv):
                          integral_max=self.integral_max, integral_punish=self.integral_punish, action_punishment=action_punishment,
                          kw=kw, kchem=kchem, ka=ka, MNaOH=MNaOH, MHA=MHA, MNH3=MNH3, qww_lo=self.qww_Vrange[0],
                          qww_hi=self.qww_Vrange[1], qc_lo=self.qc_Vrange[0], qc_hi=self.qc_Vrange[1])
-        self.vec = PHVec(self.num_envs, dtype=torch.float64, device=device, integrator=self._integrator,
+        self.vec = PHVec(self.num_envs, dtype=dtype, device=device, integrator=self._integrator,
                          seed=0 if seed is None else int(seed), **self._cfg)
         self.observation_space = Box(low=-np.full(self.m, np.inf), high=np.full(self.m, np.inf), dtype=np.float32)
         self.action_space = Box(low=-np.ones(1), high=np.ones(1), dtype=np.float32)
         self._reset_done = False
 
     def _clone_vec(self):
-        v = PHVec(self.num_envs, dtype=torch.float64, device=self._device, integrator=self._integrator, seed=self.vec.seed,
+        v = PHVec(self.num_envs, dtype=self._dtype, device=self._device, integrator=self._integrator, seed=self.vec.seed,
                   env_offset=self.vec.env_offset, **self._cfg)
         for k in ("x", "y", "r", "I", "A", "B", "C", "qww_V", "qc_V", "t", "episode", "ep_return"):
             getattr(v, k).copy_(getattr(self.vec, k))

@@ -1,0 +1,177 @@
+"""GPU tests of the agent / buffer / trainer surface (pime_b200.rl): the reference's PPO pre-pass (values, GAE, plain
+advantage -- fixtures from the reference's own compute_reward_* in tests/golden/ppo.npz) through the CUDA kernels,
+the fused explore_env into the HBM-resident replay, the learner step and the train loop."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+WT = "NonLinearWaterTankChangingParamUniformGoalIntegrator-SquareDistance-v2"
+PH = "PH1DChangingParamUniformGoalIntegrator-SqaureDistance-v35"
+
+
+def _agent_from_fixture(g, tag):
+    import pime_b200.rl as R
+    if tag == "modular":
+        agent = R.AgentResidualIntegratorModularPPO()
+        agent.init(32, 4, 1, 1)
+    else:
+        agent = R.AgentResidualPPO()
+        agent.init(32, 3, 1)
+    agent.lambda_gae_adv, agent.ratio_clip, agent.lambda_entropy = 0.95, 0.25, 0.02
+    agent.init_residual({"init_K": g[f"{tag}.K"]})
+    agent.act.load_state_dict({k[len(tag) + 6:]: torch.as_tensor(g[k]) for k in g.files if k.startswith(f"{tag}.act0.")})
+    agent.cri.load_state_dict({k[len(tag) + 6:]: torch.as_tensor(g[k]) for k in g.files if k.startswith(f"{tag}.cri0.")})
+    return agent
+
+
+@pytest.mark.parametrize("tag", ["modular", "plain"])
+def test_value_gae_and_plain_advantage_match_reference(golden, tag):
+    """agent.py:617-624,666-708: critic values by the tcgen05 kernel (fp16 operands: 2e-3), reward-to-go / GAE by the
+    scan kernel on the reference's own values (fp32: 1e-5 relative), both buffer orders (reference order = one env,
+    and the time-major order of a 6-env batch)."""
+    g = golden("ppo")
+    agent = _agent_from_fixture(g, tag)
+    state = torch.as_tensor(g[f"{tag}.state"]).cuda()
+    val = agent._values(state).cpu().numpy()
+    assert np.abs(val - g[f"{tag}.value"]).max() <= 2e-3 * max(1.0, np.abs(g[f"{tag}.value"]).max())
+    reward, mask = torch.as_tensor(g[f"{tag}.reward"]).cuda(), torch.as_tensor(g[f"{tag}.mask"]).cuda()
+    value = torch.as_tensor(g[f"{tag}.value"]).cuda()
+    L, n, T = reward.numel(), 6, 20
+    for num_envs in (1, n):
+        if num_envs == 1:
+            r_, m_, v_ = reward, mask, value
+            back = lambda x: x
+        else:   # episode-major [n, T] -> time-major [T, n] and back
+            tm = lambda x: x.view(n, T).t().contiguous().view(-1)
+            r_, m_, v_ = tm(reward), tm(mask), tm(value)
+            back = lambda x: x.view(T, n).t().contiguous().view(-1)
+        r_sum, adv = agent.compute_reward_gae(L, r_, m_, v_, num_envs)
+        np.testing.assert_allclose(back(r_sum).cpu().numpy(), g[f"{tag}.r_sum"], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(back(adv).cpu().numpy(), g[f"{tag}.adv_gae"], rtol=1e-4, atol=2e-5)
+        r_sum2, adv2 = agent.compute_reward_adv(L, r_, m_, v_, num_envs)
+        np.testing.assert_allclose(back(r_sum2).cpu().numpy(), g[f"{tag}.r_sum"], rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(back(adv2).cpu().numpy(), g[f"{tag}.adv_plain"], rtol=1e-4, atol=2e-5)
+
+
+def _make(env_id, num_envs, dtype=torch.float32, **kw):
+    import pime_b200.gym_api as G
+    import pime_b200.rl as R
+    return R.PreprocessEnv(G.make(env_id, num_envs=num_envs, dtype=dtype, **kw))
+
+
+@pytest.mark.parametrize("env_id,algo,H", [(WT, "residualintegratormodularppo", 64), (PH, "residualintegratormodularppo", 32),
+                                           ("NonLinearWaterTankChangingParamUniformGoalStacking4-SquareDistance-v2", "residualppo", 32),
+                                           (WT, "ppo", 32)])
+def test_explore_env_fills_the_hbm_replay(env_id, algo, H):
+    """agent_residual.py:52-69 as ONE launch per episode batch: row layout, masks, reward scale, a_raw = net(s) + eps*std."""
+    import pime_b200.rl as R
+    n = 300
+    env = _make(env_id, n)
+    agent = R.MODELS[algo]()
+    if "modular" in algo:
+        agent.init(H, env.state_dim, env.action_dim, env.n_integrator)
+    else:
+        agent.init(H, env.state_dim, env.action_dim)
+    if "residual" in algo:
+        agent.init_residual({"init_K": env.K.reshape(-1, 1)})
+    with torch.no_grad():
+        agent.act.net[-1].weight.normal_(0, 0.1)
+    T = env.max_step
+    buf = R.ReplayBuffer(2 * n * T, env.state_dim, 1, True, False, True, num_envs=n)
+    steps = agent.explore_env(env, buf, n * T + 1, reward_scale=0.5, gamma=0.97)
+    assert steps == 2 * n * T                                   # whole episode batches until >= target_step
+    buf.update_now_len_before_sample()
+    assert buf.now_len == steps
+    r, m, a, nz, s = buf.sample_all()
+    m_ = m.view(2 * T, n).cpu().numpy()
+    assert np.all(m_[T - 1] == 0) and np.all(m_[2 * T - 1] == 0) and np.all(np.delete(m_, [T - 1, 2 * T - 1], 0) == np.float32(0.97))
+    assert torch.isfinite(s).all() and torch.isfinite(r).all() and float(r.max()) <= 0.0
+    with torch.no_grad():
+        a_net = agent.act.a_avg(s)
+    std = float(agent.act.a_std_log.exp())
+    assert float((a - nz * std - a_net).abs().max()) <= 2e-3    # fp16 tensor-core operands vs torch fp32
+    assert 0.9 < float(nz.std()) < 1.1 and abs(float(nz.mean())) < 0.02
+    if "Stacking" not in env_id:
+        s0 = s.view(2 * T, n, -1)[0]
+        assert float(s0[:, -1].abs().max()) == 0.0 if "Integrator" in env_id else True   # I = 0 after reset
+
+
+def test_update_net_learns_and_checkpoint_roundtrip(tmp_path):
+    import pime_b200.rl as R
+    torch.manual_seed(0)
+    n = 256
+    env = _make(WT, n)
+    agent = R.AgentResidualIntegratorModularPPO()
+    agent.learning_rate = 3e-4
+    agent.init(64, env.state_dim, env.action_dim, env.n_integrator)
+    agent.init_residual({"init_K": env.K.reshape(-1, 1)})
+    buf = R.ReplayBuffer(n * env.max_step, env.state_dim, 1, True, False, True, num_envs=n)
+    before = {k: v.clone() for k, v in agent.act.state_dict().items()}
+    steps = agent.explore_env(env, buf, n * env.max_step, 1.0, 0.99)
+    obj_a, obj_c = agent.update_net(buf, steps, batch_size=4096, repeat_times=2)
+    assert np.isfinite(obj_a) and np.isfinite(obj_c)
+    after = agent.act.state_dict()
+    assert any(not torch.equal(before[k], after[k]) for k in before if k != "priorK")
+    assert torch.equal(before["priorK"], after["priorK"])                 # fix_K: the prior never trains
+    # the mean critic loss goes down when the same buffer is fitted again
+    c0 = R.logger.values["train/critic_loss"]
+    agent.update_net(buf, steps, batch_size=4096, repeat_times=8)
+    assert R.logger.values["train/critic_loss"] < c0
+    agent.save_load_model(str(tmp_path), if_save=True)
+    assert os.path.exists(tmp_path / "actor.pth") and os.path.exists(tmp_path / "critic.pth")
+    sd = torch.load(tmp_path / "actor.pth")
+    assert sorted(sd) == sorted(["a_std_log", "priorK"] + [f"{m}.{i}.{p}" for m in ("other_net", "integrator_net", "net")
+                                                          for i in (0, 2) for p in ("weight", "bias")])
+    other = R.AgentResidualIntegratorModularPPO()
+    other.init(64, env.state_dim, env.action_dim, env.n_integrator)
+    other.save_load_model(str(tmp_path), if_save=False)
+    assert all(torch.equal(other.act.state_dict()[k].cpu(), after[k].cpu()) for k in after)
+
+
+def test_zero_initialised_agent_evaluates_like_the_prior():
+    """init_actor_zero (agent_residual.py:45-50): the deterministic episodes of a fresh agent are the prior controller's."""
+    import pime_b200.rl as R
+    import pime_b200.vec as V
+    n = 512
+    env = _make(WT, n, dtype=torch.float64, noise_scale=0.0)
+    agent = R.AgentResidualIntegratorModularPPO()
+    agent.init(32, 4, 1, 1)
+    agent.init_residual({"init_K": env.K.reshape(-1, 1)})
+    env.seed(3)
+    eps = R.evaluate_batched(env, agent)
+    ref = V.WaterTankVec(n, dtype=torch.float64, noise_scale=0.0, seed=3)
+    ref.reset()
+    ref.rollout(200, -env.K, actor=None, deterministic=True)
+    got = np.array([e[0] for e in eps])
+    np.testing.assert_allclose(got, ref.ep_return.cpu().numpy(), rtol=1e-9, atol=1e-9)
+    r_avg, r_std, s_avg, _ = R.Evaluator.get_r_avg_std_s_avg_std(eps)
+    assert s_avg == 200 and r_avg < 0 and r_std > 0
+
+
+def test_train_and_evaluate_smoke(tmp_path):
+    """run.py:99-225 end to end on the pH plant (config 2 shrunk): explore -> update -> evaluate, files on disk."""
+    import pime_b200.rl as R
+    env = _make(PH, 128)
+    args = R.Arguments(if_on_policy=True)
+    args.agent = R.MODELS["residualintegratormodularppo"]()
+    args.agent.lambda_gae_adv, args.agent.ratio_clip = 0.99, 0.2
+    args.env, args.env_eval = env, _make(PH, 64)
+    args.cwd = str(tmp_path / "run")
+    args.net_dim, args.batch_size, args.repeat_times, args.target_step = 32, 1024, 2, 128 * 50
+    args.max_memo = args.target_step
+    args.break_step, args.eval_gap, args.eval_times1, args.eval_times2 = 3 * 128 * 50, 1, 64, 64
+    args.gamma, args.fix_K = 0.98, True
+    args.residual_kwargs = {"init_K": env.K.reshape(-1, 1)}
+    args.Modular_kwargs = {"integrator_dim": env.n_integrator}
+    env.target_return = 1e9
+    args.env_eval.target_return = 1e9
+    R.configure_logger(0, str(tmp_path / "tb"), "smoke")
+    agent, buf = R.train_and_evaluate(args)
+    assert buf.now_len == 128 * 50 and os.path.exists(os.path.join(args.cwd, "actor.pth"))
+    hist = [h for h in R.logger.history if "training/total_step" in h]
+    assert [h["training/total_step"] for h in hist][-1] == 3 * 128 * 50
+    assert all(np.isfinite(h.get("train/critic_loss", 0.0)) for h in hist)
