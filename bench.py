@@ -11,6 +11,8 @@ resampling).  Workload = BASELINE.json configs[2] ("1M-env water-tank ensemble r
 for N > 1 each rank owns its own 2^20 envs (weak scaling, envs sharded by global env id, no data-path
 collective; one NCCL all-reduce of the 8-double episode statistics per step).
 
+    python bench.py --workload ph    # configs[3]: pH plant, 2^23 envs over the ranks, T=50, Modular-128 (not the bench line)
+
 Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
@@ -29,10 +31,17 @@ import numpy as np  # noqa: E402
 
 METRIC = "fused env-steps/sec (plant+PI+actor)"
 UNIT = "env-steps/s"
-WORKLOAD = "1M-env water-tank ensemble rollout, fused step+PI+actor (configs[2])"
+WORKLOADS = {
+    "wt": dict(name="1M-env water-tank ensemble rollout, fused step+PI+actor (configs[2])", S=4, T=200, H=256, envs=1 << 20,
+               env="NonLinearWaterTankChangingParamUniformGoalIntegrator-SquareDistance-v2", K=[0.0, 0.4, -0.4, 0.0], sqrt=40),
+    "ph": dict(name="pH ensemble sweep, 8M envs sharded by ensemble member (configs[3])", S=3, T=50, H=128, envs=1 << 23,
+               env="PH1DChangingParamUniformGoalIntegrator-SqaureDistance-v35", K=[-0.02, 0.02, 0.035], sqrt=0),
+}
 
 FLOPS_PER_STEP = {("modular", 256, 4): 264704, ("modular", 128, 3): 66560}  # 2 x weights, SURVEY 8a d4
 TANH_PER_STEP = {("modular", 256, 4): 1025, ("modular", 128, 3): 513}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (ncu --set full), keyed by (workload, envs, T); see profiles/
+NCU_DRAM_BYTES_PER_LAUNCH = {}
 WT_STEP_BYTES_F32 = 57   # 36 B read + 21 B written per env-step, SoA fp32
 PH_STEP_BYTES_F32 = 53
 
@@ -43,9 +52,10 @@ def parse():
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
-    p.add_argument("--T", type=int, default=200, help="env steps per launch (one episode)")
-    p.add_argument("--net-dim", type=int, default=256)
+    p.add_argument("--workload", default="wt", choices=sorted(WORKLOADS))
+    p.add_argument("--envs", type=int, default=0, help="envs per GPU (default: 2^20 for wt, 2^23 / world for ph)")
+    p.add_argument("--T", type=int, default=0, help="env steps per launch (default: one episode)")
+    p.add_argument("--net-dim", type=int, default=0)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-aux", action="store_true", help="skip the stand-alone step-kernel roofline measurements")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -125,31 +135,51 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
 
 
+# ------------------------------------------------------------------------------------------------ workload resolution
+def resolve(args, world=1):
+    w = dict(WORKLOADS[args.workload])
+    w["H"] = args.net_dim or w["H"]
+    w["T"] = args.T or w["T"]
+    w["n"] = args.envs or (w["envs"] if args.workload == "wt" else max(1, w["envs"] // world))
+    w["actor"] = f"ResidualIntegratorModularPPO-{w['H']}"
+    return w
+
+
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_baseline(H, S, T, seconds, sd):
+def cpu_baseline(w, seconds, sd):
     """The oracle (C restatement of the reference loop: fp64 plant + fp32 actor, oracle/pime_oracle.c) on all host
     cores: one thread per core, each running explore-style rollouts on its own slice of envs (ctypes releases the GIL)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pime_oracle as O
     O.build()
     cores = os.cpu_count() or 1
-    per = 16  # envs per thread per chunk: 16 x 200 steps x 265 kFLOP = 0.85 GFLOP per chunk
+    H, S, T = w["H"], w["S"], w["T"]
+    per = 16  # envs per thread per chunk
     acfg = O.ActorCfg(kind=1, state_dim=S, mid_dim=H, integrator_dim=1)
     params = O.pack_actor_params(sd, 1)
-    cfg = O.wt_cfg(reward_type="square_distance")
-    priorK = -np.array([0.0, 0.4, -0.4, 0.0])
+    priorK = -np.array(w["K"])
+    is_wt = w["S"] == 4
+    cfg = O.wt_cfg(reward_type="square_distance") if is_wt else O.ph_cfg()
+    table = None if is_wt else O.ph_table()
     counts = [0] * cores
     deadline = [0.0]
 
     def work(tid):
         rng = np.random.default_rng(1000 + tid)
         while time.perf_counter() < deadline[0]:
-            h1, h2, r = rng.uniform(0, 10, per), rng.uniform(0, 10, per), rng.uniform(0, 10, per)
-            a1, a2, Kp = rng.uniform(0.0015, 0.0024, per), rng.uniform(0.0015, 0.0024, per), rng.uniform(0.07, 0.17, per)
-            I, t = np.zeros(per), np.zeros(per, np.int32)
             eps = rng.standard_normal((T, per)).astype(np.float32)
-            pn1, pn2 = rng.normal(0, 0.01, (T, per)), rng.normal(0, 0.01, (T, per))
-            O.wt_rollout(cfg, acfg, params, -0.5, priorK, 1, 0, False, T, h1, h2, r, I, t, a1, a2, Kp, eps=eps, pn1=pn1, pn2=pn2)
+            I, t = np.zeros(per), np.zeros(per, np.int32)
+            if is_wt:
+                h1, h2, r = rng.uniform(0, 10, per), rng.uniform(0, 10, per), rng.uniform(0, 10, per)
+                a1, a2, Kp = rng.uniform(0.0015, 0.0024, per), rng.uniform(0.0015, 0.0024, per), rng.uniform(0.07, 0.17, per)
+                pn1, pn2 = rng.normal(0, 0.01, (T, per)), rng.normal(0, 0.01, (T, per))
+                O.wt_rollout(cfg, acfg, params, -0.5, priorK, 1, 0, False, T, h1, h2, r, I, t, a1, a2, Kp, eps=eps, pn1=pn1, pn2=pn2)
+            else:
+                qww, qc = rng.uniform(0.005, 0.015, per), rng.uniform(0.0015, 0.0025, per)
+                A, B, Cc = O.ph_update_system(qww, qc)
+                x, r = rng.uniform(0, 50, per), rng.uniform(3, 11, per)
+                y = table[np.rint(Cc * x * 1e5).astype(np.int64)]
+                O.ph_rollout(cfg, table, acfg, params, -0.5, priorK, False, T, x, y, r, I, t, A, B, Cc, eps=eps)
             counts[tid] += per * T
     # warm-up (library load, page-in)
     deadline[0] = time.perf_counter() + 0.5
@@ -163,23 +193,23 @@ def cpu_baseline(H, S, T, seconds, sd):
     dt = time.perf_counter() - t0
     total = sum(counts)
     return {"value": total / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{total} env-steps ({total // T} episodes of T={T}, WT-Integrator + Modular-{H} actor, fp64 plant / fp32 actor, "
-                      f"C oracle, {cores} threads) in {dt:.1f} s"}
+            "sample": f"{total} env-steps ({total // T} episodes of T={T}, {'WT' if is_wt else 'pH'}-Integrator + Modular-{H} actor, "
+                      f"fp64 plant / fp32 actor, C oracle, {cores} threads) in {dt:.1f} s"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    H, S, T = args.net_dim, 4, args.T
-    sd = actor_state_dict(H, S)
+    w = resolve(args, int(os.environ.get("WORLD_SIZE", "1")))
+    sd = actor_state_dict(w["H"], w["S"])
     vals = []
     for _ in range(max(1, args.warmup)):
-        cpu_baseline(H, S, T, 1.0, sd)
+        cpu_baseline(w, 1.0, sd)
     t0 = time.perf_counter()
     last = None
     for _ in range(max(1, args.steps)):
-        last = cpu_baseline(H, S, T, max(2.0, min(args.cpu_seconds, 60.0 / max(1, args.steps))), sd)
+        last = cpu_baseline(w, max(2.0, min(args.cpu_seconds, 60.0 / max(1, args.steps))), sd)
         vals.append(last["value"])
     v = float(np.mean(vals))
     last["value"] = v
@@ -188,7 +218,7 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * (time.perf_counter() - t0) / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 plant / f32 actor",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": args.envs, "T": T, "actor": f"ResidualIntegratorModularPPO-{H}",
+            "config": {"workload": w["name"], "envs_per_gpu": w["n"], "T": w["T"], "actor": w["actor"],
                        "note": "reference algorithm (C port of the numpy/torch loop) on all host cores; each step is a bounded "
                                f"sample (~{per_step_envsteps:.3g} env-steps) of the workload"},
             "cpu_baseline": last,
@@ -213,12 +243,17 @@ def run_b200(args):
     import pime_b200.vec as V
 
     pk = peaks()
-    n, T, H, S = args.envs, args.T, args.net_dim, 4
-    K = np.array([0.0, 0.4, -0.4, 0.0])
+    w = resolve(args, world)
+    n, T, H, S = w["n"], w["T"], w["H"], w["S"]
+    is_wt = args.workload == "wt"
+    K = np.array(w["K"])
     sd = actor_state_dict(H, S)
     actor = V.ActorPack("modular", S, H, 1).update(sd)
-    env = V.WaterTankVec(n, dtype=torch.float32, obs_mode="integrator", reward_type="square_distance", noise_scale=0.01,
-                         seed=0, env_offset=rank * n)
+    if is_wt:
+        env = V.WaterTankVec(n, dtype=torch.float32, obs_mode="integrator", reward_type="square_distance", noise_scale=0.01,
+                             seed=0, env_offset=rank * n)
+    else:
+        env = V.PHVec(n, dtype=torch.float32, seed=0, env_offset=rank * n)
     env.reset()
     bs = torch.empty((T, n, S), dtype=torch.float32, device="cuda")
     bo = torch.empty((T, n, 4), dtype=torch.float32, device="cuda")
@@ -258,46 +293,52 @@ def run_b200(args):
     env.check_status()
 
     # ---- e2e: the host-buffer API call (pinned host state in, ep_return out), H2D/D2H inside the timed region
-    host = {k: getattr(env, k).detach().cpu().pin_memory() for k in ("h1", "h2", "r", "I", "a1", "a2", "Kp")}
-    host["t"] = torch.zeros(n, dtype=torch.int32).pin_memory()
-    host["episode"] = env.episode.detach().cpu().pin_memory()
-    ret_host = torch.empty(n, dtype=torch.float32).pin_memory()
-    flat_host = actor.flat.detach().cpu().pin_memory()
-    h2d = sum(v.numel() * v.element_size() for v in host.values()) + flat_host.numel() * 4
-    d2h = ret_host.numel() * 4 + 4 * n * 4 + 64
+    e2e = None
+    if is_wt:
+        host = {k: getattr(env, k).detach().cpu().pin_memory() for k in ("h1", "h2", "r", "I", "a1", "a2", "Kp")}
+        host["t"] = torch.zeros(n, dtype=torch.int32).pin_memory()
+        host["episode"] = env.episode.detach().cpu().pin_memory()
+        ret_host = torch.empty(n, dtype=torch.float32).pin_memory()
+        flat_host = actor.flat.detach().cpu().pin_memory()
+        h2d = sum(v.numel() * v.element_size() for v in host.values()) + flat_host.numel() * 4
+        d2h = ret_host.numel() * 4 + 4 * n * 4 + 64
 
-    def e2e_step():
-        actor.flat.copy_(flat_host, non_blocking=True)           # actor weights from the (host-side) learner
-        actor.update_from_flat()
-        out = env.rollout_host(host, T, -K, actor=actor, ep_return_host=ret_host, replay=(bs, bo), stats=stats)
-        return float(out["stats"].cpu()[0])                       # D2H of the step's metric (sum of episode returns)
+        def e2e_step():
+            actor.flat.copy_(flat_host, non_blocking=True)           # actor weights from the (host-side) learner
+            actor.update_from_flat()
+            out = env.rollout_host(host, T, -K, actor=actor, ep_return_host=ret_host, replay=(bs, bo), stats=stats)
+            return float(out["stats"].cpu()[0])                       # D2H of the step's metric (sum of episode returns)
 
-    e2e_steps = max(2, min(args.steps, 3))
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+        e2e_steps = max(2, min(args.steps, 3))
         e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * T * e2e_steps / float(e2e_t.item())
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * T * e2e_steps / float(e2e_t.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h),
+               "api": "WaterTankVec.rollout_host -> pime_wt_rollout_host_f32 (pinned host state in, ep_return + final state out)"}
 
+    kname = f"rollout_kernel<{'WtGlue' if is_wt else 'PhGlue'}<float>, modular, {H}>"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (plant, prior, obs; actor: f16 tensor-core operands, f32 accumulate)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "T": T, "actor": f"ResidualIntegratorModularPPO-{H}",
-                       "env": "NonLinearWaterTankChangingParamUniformGoalIntegrator-SquareDistance-v2", "noise_scale": 0.01,
+            "dtype": "f32 (plant, prior, obs, first and last actor layer; hidden layers: f16 tensor-core operands, f32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": w["name"], "envs_per_gpu": n, "T": T, "actor": w["actor"], "env": w["env"],
+                       "noise_scale": 0.01 if is_wt else 0.0,
                        "policy": "stochastic (explore_env)", "replay": "GPU-resident, time-major [T,n,S]+[T,n,4] fp32",
                        "l2": f"each step streams {(bs.numel() + bo.numel()) * 4 / 1e9:.2f} GB of replay rows through L2 (>> 126 MB), "
                              "which flushes it between timed steps",
                        "sharding": "contiguous env-id ranges per rank, Philox keyed by global env id"},
             "clocks": clocks, "gpu_launches": args.steps,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "WaterTankVec.rollout_host -> pime_wt_rollout_host_f32 (pinned host state in, ep_return + final state out)"},
             "episode_stats": {"mean_return": st[0] / max(st[2], 1), "episodes": st[2]}}
+    if e2e:
+        line["e2e"] = e2e
 
     if rank == 0:
         flops = FLOPS_PER_STEP.get(("modular", H, S))
@@ -305,18 +346,20 @@ def run_b200(args):
         if flops:
             ach = n * T * flops / (step_ms * 1e-3) / 1e12
             line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                                "traffic": None, "kernel": f"rollout_kernel<WtGlue<float>, modular, {H}>",
-                                "peak_source": pk["src"] + ", sustained bf16 (kernel runs for >100 ms)",
-                                "note": "co-limited by the MUFU pipe (1025 tanh + 40 sqrt per env-step), see sfu"}
+                                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((args.workload, n, T)), "kernel": kname,
+                                "peak_source": pk["src"] + ", sustained bf16 (kernel runs for >50 ms)",
+                                "note": "the binding unit is the MUFU pipe (one tanh per hidden activation), see sfu; HBM traffic is "
+                                        "the replay rows only (traffic = dram bytes of one launch, ncu --set full, profiles/)"}
             sm_mhz = clocks.get("sm_mhz") or pk["sm_max"]
-            mufu = n * T * (TANH_PER_STEP[("modular", H, S)] + 40 + 6) / (step_ms * 1e-3)
+            mufu = n * T * (TANH_PER_STEP[("modular", H, S)] - 1 + w["sqrt"] + 6) / (step_ms * 1e-3)
             mufu_peak = 148 * 16 * sm_mhz * 1e6
             line["sfu"] = {"achieved_gops": mufu / 1e9, "peak_gops": mufu_peak / 1e9, "frac": mufu / mufu_peak,
-                           "note": "MUFU ops/s vs 148 SM x 16/clk at the median SM clock under load"}
-        if not args.no_aux:
+                           "note": "MUFU ops/s (hidden tanh + plant sqrt + Box-Muller) vs 148 SM x 16/clk at the median SM clock "
+                                   "under load (tanh.approx microbenchmark on this pool: 16.3 per clk per SM)"}
+        if not args.no_aux and is_wt:
             line["roofline_step"] = aux_step_rooflines(V, pk)
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(H, S, T, args.cpu_seconds, sd)
+            line["cpu_baseline"] = cpu_baseline(w, args.cpu_seconds, sd)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
