@@ -326,7 +326,8 @@ def run_b200(args):
 
     kname = f"rollout_kernel<{'WtGlue' if is_wt else 'PhGlue'}<float>, modular, {H}>"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak" if is_wt or args.envs else "strong", "vs_baseline": None,
             "dtype": "f32 (plant, prior, obs, first and last actor layer; hidden layers: f16 tensor-core operands, f32 accumulate)",
             "data": "synthetic",
             "config": {"workload": w["name"], "envs_per_gpu": n, "T": T, "actor": w["actor"], "env": w["env"],

@@ -369,7 +369,7 @@ template <int KIND, int H> struct Engine {
     using G = Geo<KIND, H>;
     uint8_t *sA, *sRing;
     const Blk *tbl;
-    uint64_t *full, *empty, *a_rdy, *a_free, *o_rdy, *d_ready, *out_rdy;
+    uint64_t *full, *empty, *a_rdy, *a_free, *o_rdy, *d_ready, *out_rdy, *h_rdy;
     float *sOutW, *sPart;
     uint32_t *tmem_slot;
     uint32_t tmem_base;
@@ -389,7 +389,8 @@ template <int KIND, int H> struct Engine {
         o_rdy = a_free + kMaxChunks;
         d_ready = o_rdy + 2;
         out_rdy = d_ready + 1;
-        tmem_slot = reinterpret_cast<uint32_t *>(out_rdy + 1);
+        h_rdy = out_rdy + 1;
+        tmem_slot = reinterpret_cast<uint32_t *>(h_rdy + 1);
         sOutW = reinterpret_cast<float *>(smem + G::OutWOff);
         sPart = reinterpret_cast<float *>(smem + G::PartOff);
         const int tid = threadIdx.x;
@@ -400,6 +401,7 @@ template <int KIND, int H> struct Engine {
             mbar_init(&o_rdy[1], kOwnerThreads);
             mbar_init(d_ready, 1);
             mbar_init(out_rdy, kWorkerThreads);
+            mbar_init(h_rdy, 1);
             fence_barrier_init();
         }
         if (tid / 32 == kMmaWarp) tmem_alloc(tmem_slot, G::TmemCols);
@@ -520,9 +522,9 @@ template <int KIND, int H> struct Engine {
                 blk<H, true>(obs, 1, Da);                              // P0: other_net.0 -> Da (Da was released by the third epilogue)
                 if (q > 0) { mbar_wait(out_rdy, ((uint32_t)q - 1u) & 1u); tc_fence_after(); }   // last epilogue of the previous pass has read Db
                 blk<H, true>(obs, 1, Db, d_ready);                     //     integrator_net.0 -> Db
-                layer<Hh, true>(Da, apar, (Hh + 63) / 64, nullptr, nullptr);   // P1: other_net.2 -> Da[0:H/2], behind the epilogue of Da
+                layer<Hh, true>(Da, apar, (Hh + 63) / 64, h_rdy, nullptr);     // P1: other_net.2 -> Da[0:H/2], behind the epilogue of Da
                 apar ^= 1;
-                layer<Hh, false>(Da + Hh, apar, 0, d_ready, nullptr);  // P2: integrator_net.2 -> Da[H/2:H], behind the epilogue of Db
+                layer<Hh, true>(Da + Hh, apar, 0, d_ready, nullptr);   // P2: integrator_net.2 -> Da[H/2:H], behind the epilogue of Db
                 apar ^= 1;
                 layer<H, false>(Db, apar, 0, d_ready, nullptr);        // P3: net.0 on cat -> Db; net.2 is the workers' dot product
                 apar ^= 1;
@@ -550,17 +552,20 @@ template <int KIND, int H> struct Engine {
     }
     // A[:, 32j .. 32j+32) = act(D[:, dcol + 32j ..)) for the 32-column pieces j of this half (even / odd); the bias
     // is already in D.  Piece j belongs to chunk j/2, whose barrier collects both halves.
-    // WAIT_FREE: the previous reader of the A chunk may still be in flight (no d_ready wait in between): wait a_free.
-    template <bool WAIT_FREE> __device__ __forceinline__ void epilogue(int row, int half, int dcol, uint32_t free_parity) {
+    // WAIT_FREE: the previous reader of the A chunk may still be in flight (no d_ready wait in between): wait a_free
+    // (a_free[c] completes twice per pass: other_net.2 and integrator_net.2 each release chunk c once they have read it).
+    template <bool WAIT_FREE, int JB = 0, int JE = G::NP>
+    __device__ __forceinline__ void epilogue(int row, int half, int dcol, uint32_t free_parity) {
         const uint32_t taddr = tmem_base + ((uint32_t)((row / 32) * 32) << 16) + (uint32_t)dcol;
         float v[2][32];
-        if (half < G::NP) tmem_ld32_issue(taddr + half * 32, v[0]);
+        const int j0 = JB + ((half - JB) & 1);   // first piece of this half inside [JB, JE)
+        if (j0 < JE) tmem_ld32_issue(taddr + j0 * 32, v[0]);
 #pragma unroll
-        for (int it = 0; it < (G::NP + 1) / 2; ++it) {
-            const int j = half + 2 * it;
-            if (j < G::NP) {
+        for (int it = 0; it < (JE - JB + 1) / 2; ++it) {
+            const int j = j0 + 2 * it;
+            if (j < JE) {
                 tmem_wait_ld();
-                if (j + 2 < G::NP) tmem_ld32_issue(taddr + (j + 2) * 32, v[(it + 1) & 1]);
+                if (j + 2 < JE) tmem_ld32_issue(taddr + (j + 2) * 32, v[(it + 1) & 1]);
                 float(&x)[32] = v[it & 1];
 #pragma unroll
                 for (int e = 0; e < 32; ++e) x[e] = act_fn<G::kRelu>(x[e]);
@@ -618,9 +623,12 @@ template <int KIND, int H> struct Engine {
             if constexpr (G::kModular) {
                 wait_d();                                             // P0: Da = other_net.0, Db = integrator_net.0 (net_residual.py:151,154)
                 epilogue<false>(row, half, 0, 0);                     // tanh(Da) -> A, feeds other_net.2 (:152)
-                epilogue<true>(row, half, H, (uint32_t)q & 1u);       // tanh(Db) -> A, feeds integrator_net.2 (:155)
-                wait_d();                                             // P2: Da = cat pre-activation (:170)
-                epilogue<false>(row, half, 0, 0);                     // feeds net.0 (:157)
+                epilogue<true>(row, half, H, 0u);                     // tanh(Db) -> A, feeds integrator_net.2 (:155)
+                mbar_wait(h_rdy, (uint32_t)q & 1u);                   // P1: Da[0:H/2] = other_net.2 (complete long ago)
+                tc_fence_after();
+                epilogue<true, 0, G::NP / 2>(row, half, 0, 1u);       // first half of cat (:170) while integrator_net.2 finishes
+                wait_d();                                             // P2: Da[H/2:H] = integrator_net.2
+                epilogue<true, G::NP / 2, G::NP>(row, half, 0, 1u);   // second half of cat, feeds net.0 (:157)
                 wait_d();                                             // P3: Db = net.0
                 epilogue_dot(row, half, H, q & 1);                    // net.2 (:158)
             } else {
