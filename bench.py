@@ -41,7 +41,8 @@ WORKLOADS = {
 FLOPS_PER_STEP = {("modular", 256, 4): 264704, ("modular", 128, 3): 66560}  # 2 x weights, SURVEY 8a d4
 TANH_PER_STEP = {("modular", 256, 4): 1025, ("modular", 128, 3): 513}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (ncu --set full), keyed by (workload, envs, T); see profiles/
-NCU_DRAM_BYTES_PER_LAUNCH = {}
+NCU_DRAM_BYTES_PER_LAUNCH = {("wt", 1 << 20, 200): 6.7797e9}   # profiles/r01_ncu_summary.md (algorithmic: 6.71e9 replay rows)
+NCU_DRAM_BYTES_STEP = {"wt": 2.1359e9}   # wt_step_kernel<float>, 2^25 envs (algorithmic 1.913e9 + 8 B/env ep_return)
 WT_STEP_BYTES_F32 = 57   # 36 B read + 21 B written per env-step, SoA fp32
 PH_STEP_BYTES_F32 = 53
 
@@ -406,7 +407,8 @@ def aux_step_rooflines(V, pk):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         gbs = n * nbytes / (ms * 1e-3) / 1e9
-        out[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+        out[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                     "traffic": NCU_DRAM_BYTES_STEP.get(name),
                      "env_steps_per_s": n / (ms * 1e-3), "bytes_per_env_step": nbytes, "envs": n,
                      "kernel": f"{name}_step_kernel<float>", "peak_source": pk["src"]}
         del env
