@@ -1,0 +1,177 @@
+"""GPU tests of the gym-style drop-in surface (pime_b200.gym_api): the reference's env ids, gym API, ensemble and test
+API driven by the CUDA kernels, pinned on the KATs of SURVEY.md section 8c (values printed by the reference), plus
+size-independent properties at the BASELINE size (2^20 envs)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+WT_INT = "NonLinearWaterTankChangingParamUniformGoalIntegrator-SquareDistance-v2"
+PH_INT = "PH1DChangingParamUniformGoalIntegrator-SqaureDistance-v35"
+
+
+@pytest.fixture(scope="module")
+def G():
+    import pime_b200.gym_api as G
+    return G
+
+
+def test_all_registered_ids_construct_with_reference_shapes(G):
+    want = {"PH1DChangingParamUniformGoalIntegrator-SqaureDistance-v35": (3, 50),
+            "PH1DChangingParamUniformGoalIntegrator-SqaureDistance-NoIB-v35": (3, 50),
+            "NonLinearWaterTankChangingParamUniformGoal-SquareDistance-v2": (3, 200),
+            "NonLinearWaterTankChangingParamUniformGoalIntegrator-SquareDistance-v2": (4, 200),
+            "NonLinearWaterTankChangingParamUniformGoalStacking4-SquareDistance-v2": (12, 200),
+            "NonLinearWaterTankChangingParamUniformGoalStacking10-SquareDistance-v2": (30, 200),
+            "NonLinearWaterTankChangingParamUniformGoalStacking1-SquareDistance-v2": (3, 200)}
+    assert set(G.REGISTRY) == set(want)                                  # gym_control/__init__.py:3-142
+    import pime_b200.rl as R
+    for env_id, (S, T) in want.items():
+        env = G.make(env_id)
+        assert env.unwrapped.spec.id == env_id
+        obs = env.reset()
+        assert obs.shape == (S,) and obs.dtype == np.float64 and env.observation_space.shape == (S,)
+        assert env.action_space.shape == (1,) and float(env.action_space.high[0]) == 1.0
+        o2, rew, done, info = env.step(np.array([0.1]))
+        assert o2.shape == (S,) and isinstance(rew, float) and isinstance(done, bool) and info == {}
+        # the reference registers a 4-entry K for the 3-observation id (gym_control/__init__.py:46) -- kept as is
+        assert env.K.shape == ((4,) if env_id == "NonLinearWaterTankChangingParamUniformGoal-SquareDistance-v2" else (S,))
+        assert env.seed(5) == [5]
+        assert R.PreprocessEnv(env).max_step == T                        # elegantrl/env.py:221-231
+
+
+def test_kat1_water_tank_through_the_gym_api(G):
+    """bit-identical to the reference's printed trajectory."""
+    env = G.make(WT_INT, reward_type="distance", noise_scale=0.0)
+    env.reset()
+    env.reset_changable_parameters(0.0019, 0.0019, 0.12)
+    env.set_state(0.0, 0.0)
+    env.set_r(3.0)
+    env.integrator = 0.0
+    obs = env._get_observe()
+    rows = [(1.2000000000000002, 2.4692863612658598, 0.1371267442911145, 2.8628732557088856, -2.8628732557088856),
+            (1.1451493022835542, 4.727828693028896, 0.3706586062224364, 5.492214649486449, -2.6293413937775636),
+            (1.0517365575110256, 6.788364667539474, 0.6534380242159421, 7.838776625270507, -2.346561975784058),
+            (0.9386247903136232, 8.648875526100547, 0.9689474740993569, 9.86982915117115, -2.031052525900643)]
+    priorK = -env.K.reshape(-1, 1)
+    for action, h1, h2, I, rew in rows:
+        a = obs @ priorK
+        assert float(a[0]) == action
+        obs, r, done, _ = env.step(a)
+        assert (obs[0], obs[1], obs[3], r) == (h1, h2, I, rew) and not done
+    assert env.get_changable_parameters() == (0.0019, 0.0019, 0.12)
+    assert (env.h1, env.h2, env.r, env.integrator) == (rows[-1][1], rows[-1][2], 3.0, rows[-1][3])
+
+
+def test_kat4_ph_through_the_gym_api(G):
+    """SURVEY 8c KAT-4 (x' = A x + B u bit-identical; y through the device-built table: 1e-12)."""
+    env = G.make(PH_INT)
+    env.reset()
+    env.set_params(0.01, 0.002)
+    env.update_system()                       # the reference's set_params does NOT refresh dsys
+    env.set_state(0.0)
+    env.set_r(7.0)
+    env.integrator = 0.0
+    obs = env._get_observe()
+    rows = [(0.09404057651683974, 14.873693355550358, 2.0108812493180586, 4.989118750681941, -24.89130590840613),
+            (-0.2744015312875068, 22.042201761386956, 1.6183247937618077, 10.370793956920133, -28.96242802543889),
+            (-0.47061129261696855, 25.243770371322867, 1.5158308962973068, 15.854963060622826, -30.0761107580072),
+            (-0.6646070891958528, 25.227582653974668, 1.5162583986482367, 21.33870466197459, -30.071421950396),
+            (-0.856529495196146, 22.605107021724443, 1.5984100713155363, 25.0, -29.177173757665432),
+            (-0.9830317985736894, 18.73818227736746, 1.7574230444634973, 25.0, -27.484613134722387)]
+    priorK = -env.K.reshape(-1, 1)
+    for action, x, y, I, rew in rows:
+        a = obs @ priorK
+        assert abs(float(a[0]) - action) <= 1e-11
+        obs, r, done, _ = env.step(a)
+        assert abs(env.state - x) <= 1e-9 * x
+        np.testing.assert_allclose([obs[0], obs[2], r], [y, I, rew], rtol=1e-10, atol=1e-10)
+
+
+def test_kat5_stacking_frames(G):
+    env = G.make("NonLinearWaterTankChangingParamUniformGoalStacking4-SquareDistance-v2", noise_scale=0.0)
+    obs = env.reset()
+    assert np.array_equal(obs, np.tile(obs[:3], 4)) and env.m == 12
+    assert np.array_equal(env.K, np.array([0.0] * 9 + [0.0, 0.4, -0.4]))
+    o2, _, _, _ = env.step(np.array([0.3]))
+    assert np.array_equal(o2[:9], obs[:9]) and not np.array_equal(o2[9:11], obs[9:11]) and o2[11] == obs[11]
+
+
+def test_reference_error_behaviour(G):
+    env = G.make(WT_INT)
+    with pytest.raises(AssertionError):       # "Please reset the env first" (nonlinear_watertank.py:794)
+        env.step(np.array([0.0]))
+    ph = G.make(PH_INT)
+    ph.reset()
+    with pytest.raises(IndexError):           # table overflow (ph.py:188)
+        ph.set_state(1e9)
+    with pytest.raises(NotImplementedError):
+        G.make(WT_INT, reset_from_last_state=True)
+
+
+def test_deepcopy_gives_an_independent_env(G):
+    """utils/test.py:1058-1059 and utils/robust_test.py:5 deep-copy the env."""
+    env = G.make(WT_INT, noise_scale=0.0)
+    env.reset()
+    twin = copy.deepcopy(env)
+    a = np.array([0.25])
+    o1, r1, _, _ = env.step(a)
+    o2, r2, _, _ = twin.step(a)
+    assert np.array_equal(o1, o2) and r1 == r2
+    env.step(a)
+    assert twin._episode_steps == 1 and env._episode_steps == 2
+
+
+def test_ensemble_resampling_and_reset_r(G):
+    env = G.make(WT_INT)
+    env.seed(11)
+    env.reset()
+    p0 = env.get_changable_parameters()
+    env.reset()
+    p1 = env.get_changable_parameters()
+    assert p0 != p1 and all(lo <= v <= hi for v, (lo, hi) in zip(p1, ([0.0015, 0.0024], [0.0015, 0.0024], [0.07, 0.17])))
+    env.set_reset_all(False)                  # README.md:27-33: keep the ensemble member, new state / set-point only
+    env.reset()
+    assert env.get_changable_parameters() == p1 and env.integrator == 0.0 and env._episode_steps == 0
+
+
+def test_full_size_properties_at_2_pow_20_envs():
+    """Size-independent properties at the BASELINE size: (a) zero-initialised actor == prior-only policy, bit for bit;
+    (b) any split of the env-id range reproduces the unsplit run (Philox keyed by global env id); (c) done exactly at
+    t = 200 and in-kernel auto-reset restarts every env."""
+    import pime_b200.vec as V
+    n, T = 1 << 20, 200
+    K = np.array([0.0, 0.4, -0.4, 0.0])
+    H = 256
+    sd = {}
+    rng = np.random.default_rng(0)
+    for name, o, i in [("other_net.0", H, 3), ("other_net.2", H // 2, H), ("integrator_net.0", H, 1),
+                       ("integrator_net.2", H // 2, H), ("net.0", H, H), ("net.2", 1, H)]:
+        b = 1.0 / np.sqrt(i)
+        sd[name + ".weight"] = rng.uniform(-b, b, (o, i)).astype(np.float32)
+        sd[name + ".bias"] = rng.uniform(-b, b, o).astype(np.float32)
+    sd["net.2.weight"][:] = 0.0
+    sd["net.2.bias"][:] = 0.0                                              # init_actor_zero (agent_residual.py:45-50)
+    actor = V.ActorPack("modular", 4, H, 1).update(sd)
+
+    def run(n_, off, use_actor):
+        env = V.WaterTankVec(n_, dtype=torch.float32, seed=7, env_offset=off, noise_scale=0.01)
+        env.reset()
+        stats = torch.zeros(8, dtype=torch.float64, device="cuda")
+        env.rollout(T + 3, -K, actor=actor if use_actor else None, deterministic=True, auto_reset=True, stats=stats)
+        return env, stats.cpu().numpy()
+
+    whole, st = run(n, 0, True)
+    prior, st_p = run(n, 0, False)
+    assert torch.equal(whole.h2, prior.h2) and torch.equal(whole.ep_return, prior.ep_return)
+    np.testing.assert_allclose(st, st_p, rtol=1e-12)                        # per-env data bit-equal; the sums differ by atomicAdd order
+    assert st[2] == n and st[5] == n * (T + 3) and int(whole.t.min()) == 3 == int(whole.t.max())   # one episode each, then reset
+    assert int(whole.episode.min()) == 2                                                            # reset() + in-kernel reset
+    lo, _ = run(n // 2, 0, True)
+    hi, _ = run(n // 2, n // 2, True)
+    assert torch.equal(torch.cat([lo.h2, hi.h2]), whole.h2) and torch.equal(torch.cat([lo.ep_return, hi.ep_return]), whole.ep_return)
+    mean_ret = st[0] / st[2]
+    assert -4000 < mean_ret < -500                                          # the P prior on random set-points (SquareDistance)
