@@ -36,6 +36,9 @@ WORKLOADS = {
                env="NonLinearWaterTankChangingParamUniformGoalIntegrator-SquareDistance-v2", K=[0.0, 0.4, -0.4, 0.0], sqrt=40),
     "ph": dict(name="pH ensemble sweep, 8M envs sharded by ensemble member (configs[3])", S=3, T=50, H=128, envs=1 << 23,
                env="PH1DChangingParamUniformGoalIntegrator-SqaureDistance-v35", K=[-0.02, 0.02, 0.035], sqrt=0),
+    "train": dict(name="full PIME residual actor-critic training, GPU-resident replay, grad allreduce (configs[4])", S=4, T=200, H=256,
+                  envs=1 << 16, env="NonLinearWaterTankChangingParamUniformGoalIntegrator-SquareDistance-v2",
+                  K=[0.0, 0.4, -0.4, 0.0], sqrt=40),
 }
 
 FLOPS_PER_STEP = {("modular", 256, 4): 264704, ("modular", 128, 3): 66560}  # 2 x weights, SURVEY 8a d4
@@ -60,6 +63,9 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-aux", action="store_true", help="skip the stand-alone step-kernel roofline measurements")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--batch-size", type=int, default=1 << 17, help="train workload: PPO minibatch rows")
+    p.add_argument("--repeat-times", type=int, default=2, help="train workload: PPO epochs over the buffer")
+    p.add_argument("--tf32", action="store_true", help="train workload: TF32 cuBLAS GEMMs in the learner (default: fp32 like the reference)")
     return p.parse_args()
 
 
@@ -141,7 +147,7 @@ def resolve(args, world=1):
     w = dict(WORKLOADS[args.workload])
     w["H"] = args.net_dim or w["H"]
     w["T"] = args.T or w["T"]
-    w["n"] = args.envs or (w["envs"] if args.workload == "wt" else max(1, w["envs"] // world))
+    w["n"] = args.envs or (max(1, w["envs"] // world) if args.workload == "ph" else w["envs"])
     w["actor"] = f"ResidualIntegratorModularPPO-{w['H']}"
     return w
 
@@ -416,10 +422,77 @@ def aux_step_rooflines(V, pk):
     return out
 
 
+def run_train(args):
+    """configs[4]: explore (one fused launch) -> update_net (values + GAE kernels, torch-autograd minibatches, flat grad
+    all-reduce) per step; reports transitions/s end to end and the rollout share.  Not the bench line."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import pime_b200.gym_api as G
+    import pime_b200.rl as R
+    w = resolve(args, world)
+    n, T, H = w["n"], w["T"], w["H"]
+    env = R.PreprocessEnv(G.make(w["env"], num_envs=n, dtype=torch.float32))
+    env.env.vec.env_offset = rank * n
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    agent = R.AgentResidualIntegratorModularPPO()
+    agent.learning_rate = 3e-4
+    agent.init(H, env.state_dim, env.action_dim, env.n_integrator)
+    agent.init_residual({"init_K": env.K.reshape(-1, 1)})
+    buf = R.ReplayBuffer(n * T, env.state_dim, 1, True, False, True, num_envs=n)
+    t_roll = t_upd = 0.0
+
+    def step():
+        nonlocal t_roll, t_upd
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        steps = agent.explore_env(env, buf, n * T, 1.0, 0.99)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        agent.update_net(buf, steps, args.batch_size, args.repeat_times)
+        torch.cuda.synchronize()
+        t_roll += t1 - t0
+        t_upd += time.perf_counter() - t1
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    t_roll = t_upd = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    if world > 1:
+        dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"metric": "PPO training transitions/sec (explore + update)", "value": world * n * T * args.steps / float(dt.item()),
+                          "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "config": {"workload": w["name"], "envs_per_gpu": n, "T": T, "actor": w["actor"], "batch_size": args.batch_size,
+                                     "repeat_times": args.repeat_times,
+                                     "minibatches_per_step": int(args.repeat_times * n * T / args.batch_size),
+                                     "learner": "values + GAE: CUDA kernels; minibatch step: torch autograd (cuBLAS, "
+                                                + ("TF32" if args.tf32 else "fp32") + ")"},
+                          "rollout_share": t_roll / (t_roll + t_upd), "rollout_ms_per_step": 1e3 * t_roll / args.steps,
+                          "update_ms_per_step": 1e3 * t_upd / args.steps}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     else:
         run_b200(args)
 

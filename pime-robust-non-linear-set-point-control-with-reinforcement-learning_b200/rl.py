@@ -296,6 +296,9 @@ class AgentPPO:
         self.priorK = None
         self._n_updates = 0
         self._packs = {}
+        self._graph = None
+        self.use_cuda_graph = True      # record the minibatch step into a CUDA graph when it is launch bound
+        self.graph_max_batch = 8192
 
     # ---- construction
     def _make_actor(self, net_dim, state_dim, action_dim, **kw):
@@ -313,8 +316,11 @@ class AgentPPO:
         self.priorK = np.zeros((state_dim, 1))
 
     def _new_optimizer(self):
+        # capturable: the minibatch step can be recorded into a CUDA graph (same arithmetic as the eager step)
         self.optimizer = torch.optim.Adam([{"params": self.act.parameters(), "lr": self.learning_rate},
-                                           {"params": self.cri.parameters(), "lr": self.learning_rate}])
+                                           {"params": self.cri.parameters(), "lr": self.learning_rate}],
+                                          capturable=self.device is not None and self.device.type == "cuda")
+        self._graph = None
 
     def init_actor_zero(self):
         """agent_residual.py:45-50: last layer zeroed -> the policy starts exactly at the prior."""
@@ -447,19 +453,32 @@ class AgentPPO:
             buf_logprob = -(buf_noise.pow(2) * 0.5 + self.act.a_std_log + self.act.sqrt_2pi_log).sum(1)
             buf_r_sum, buf_advantage = self.compute_reward(buf_len, buf_reward, buf_mask, buf_value, buffer.num_envs)
         params = [p for g in self.optimizer.param_groups for p in g["params"]]
-        obj_actor = obj_critic = None
-        sums = torch.zeros(4, device=self.device)
         iters = int(repeat_times * buf_len / batch_size)
-        for _ in range(iters):
+        data = (buf_state, buf_action, buf_r_sum, buf_logprob, buf_advantage)
+
+        def minibatch(src, out):
             idx = torch.randint(buf_len, size=(batch_size,), device=self.device)
-            obj_actor, obj_critic, obj_united, obj_entropy = self.ppo_objectives(
-                buf_state[idx], buf_action[idx], buf_r_sum[idx], buf_logprob[idx], buf_advantage[idx])
-            self.optimizer.zero_grad()
+            obj_actor, obj_critic, obj_united, obj_entropy = self.ppo_objectives(*(t[idx] for t in src))
+            self.optimizer.zero_grad(set_to_none=False)
             obj_united.backward()
             if _dist_on():
                 allreduce_mean_grads(params)
             self.optimizer.step()
-            sums += torch.stack([obj_united.detach(), obj_actor.detach(), obj_critic.detach(), obj_entropy.detach()])
+            out.copy_(torch.stack([obj_united.detach(), obj_actor.detach(), obj_critic.detach(), obj_entropy.detach()]))
+
+        sums = torch.zeros(4, device=self.device)
+        last = torch.zeros(4, device=self.device)
+        use_graph = self.use_cuda_graph and iters >= 8 and batch_size <= self.graph_max_batch and not _dist_on()
+        if use_graph:
+            g = self._graphed_step(minibatch, data, buf_len, batch_size)
+            for _ in range(iters):
+                g.replay()
+                sums += self._graph["out"]
+            last = self._graph["out"].clone()
+        else:
+            for _ in range(iters):
+                minibatch(data, last)
+                sums += last
         self._n_updates += int(repeat_times)
         if iters:
             u, a, c, e = (sums / iters).tolist()
@@ -467,8 +486,44 @@ class AgentPPO:
             logger.record("train/actor_loss", a)
             logger.record("train/critic_loss", c)
             logger.record("train/entropy_losses", e)
-            return float(obj_actor), float(obj_critic)
+            return float(last[1]), float(last[2])
         return 0.0, 0.0
+
+    def _graphed_step(self, minibatch, data, buf_len, batch_size):
+        """One PPO minibatch (index draw, gather, forward, backward, Adam) recorded ONCE into a CUDA graph and replayed:
+        the reference's configurations (batch 128-512) are launch-latency bound (~60 small kernels per minibatch).
+        The graph reads static copies of the buffer tensors; it is re-recorded when a shape changes."""
+        key = (buf_len, batch_size, tuple(t.shape for t in data))
+        if self._graph is None or self._graph["key"] != key:
+            static = tuple(torch.empty_like(t) for t in data)
+            out = torch.zeros(4, device=self.device)
+            for s, t in zip(static, data):
+                s.copy_(t)
+            # snapshot: the warm-up iterations and the capture itself must not change the training state; everything is
+            # restored IN PLACE because the recorded graph holds the addresses of the parameters and Adam moments
+            plist = [p for grp in self.optimizer.param_groups for p in grp["params"]]
+            p_snap = [p.detach().clone() for p in plist]
+            o_snap = {id(p): {k: v.clone() for k, v in self.optimizer.state.get(p, {}).items() if torch.is_tensor(v)} for p in plist}
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    minibatch(static, out)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                minibatch(static, out)
+            with torch.no_grad():
+                for p, snap in zip(plist, p_snap):
+                    p.copy_(snap)
+                    for k, v in self.optimizer.state.get(p, {}).items():
+                        if torch.is_tensor(v):
+                            v.copy_(o_snap[id(p)][k]) if k in o_snap[id(p)] else v.zero_()
+            self._graph = {"key": key, "graph": graph, "static": static, "out": out}
+        else:
+            for s, t in zip(self._graph["static"], data):
+                s.copy_(t)
+        return self._graph["graph"]
 
     # ---- checkpoints (agent.py:86-114): same file names and state-dict keys as the reference
     def save_load_model(self, cwd, if_save):

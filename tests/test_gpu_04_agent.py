@@ -92,7 +92,7 @@ def test_explore_env_fills_the_hbm_replay(env_id, algo, H):
     assert torch.isfinite(s).all() and torch.isfinite(r).all() and float(r.max()) <= 0.0
     with torch.no_grad():
         a_net = agent.act.a_avg(s)
-    std = float(agent.act.a_std_log.exp())
+    std = float(agent.act.a_std_log.detach().exp())
     assert float((a - nz * std - a_net).abs().max()) <= 2e-3    # fp16 tensor-core operands vs torch fp32
     assert 0.9 < float(nz.std()) < 1.1 and abs(float(nz.mean())) < 0.02
     if "Stacking" not in env_id:
@@ -175,3 +175,47 @@ def test_train_and_evaluate_smoke(tmp_path):
     hist = [h for h in R.logger.history if "training/total_step" in h]
     assert [h["training/total_step"] for h in hist][-1] == 3 * 128 * 50
     assert all(np.isfinite(h.get("train/critic_loss", 0.0)) for h in hist)
+
+
+def test_cuda_graph_minibatch_step_is_transparent():
+    """The recorded minibatch step (index draw + gather + forward + backward + Adam) leaves the training state untouched
+    while it is being recorded, and trains like the eager step (same kernels, different index draws)."""
+    import pime_b200.rl as R
+    n = 64
+    env = _make(WT, n)
+    finals = {}
+    for mode in (False, True):
+        torch.manual_seed(0)
+        env.seed(0)
+        agent = R.AgentResidualIntegratorModularPPO()
+        agent.learning_rate = 3e-4
+        agent.use_cuda_graph = mode
+        agent.init(32, env.state_dim, env.action_dim, env.n_integrator)
+        agent.init_residual({"init_K": env.K.reshape(-1, 1)})
+        buf = R.ReplayBuffer(n * env.max_step, env.state_dim, 1, True, False, True, num_envs=n)
+        steps = agent.explore_env(env, buf, n * env.max_step, 1.0, 0.99)
+        if mode:   # recording alone must be a no-op on parameters and Adam state
+            before = [p.detach().clone() for p in agent.act.parameters()] + [p.detach().clone() for p in agent.cri.parameters()]
+            buf.update_now_len_before_sample()
+            r, m, a, nz, s = buf.sample_all()
+            data = (s, a, torch.zeros_like(r), torch.zeros_like(r), torch.zeros_like(r))
+
+            def mb(src, out):
+                idx = torch.randint(steps, size=(256,), device=agent.device)
+                oa, oc, ou, oe = agent.ppo_objectives(*(t[idx] for t in src))
+                agent.optimizer.zero_grad(set_to_none=False)
+                ou.backward()
+                agent.optimizer.step()
+                out.copy_(torch.stack([ou.detach(), oa.detach(), oc.detach(), oe.detach()]))
+            agent._graphed_step(mb, data, steps, 256)
+            after = list(agent.act.parameters()) + list(agent.cri.parameters())
+            assert all(torch.equal(x, y) for x, y in zip(before, after))
+            assert all(float(v.abs().max()) == 0.0 for st in agent.optimizer.state.values() for v in st.values() if torch.is_tensor(v))
+            agent._graph = None
+        agent.update_net(buf, steps, batch_size=256, repeat_times=1)
+        c0 = R.logger.values["train/critic_loss"]
+        agent.update_net(buf, steps, batch_size=256, repeat_times=4)
+        finals[mode] = (c0, R.logger.values["train/critic_loss"])
+        assert finals[mode][1] < finals[mode][0]
+        assert (agent._graph is not None) == mode
+    assert abs(finals[True][1] - finals[False][1]) <= 0.25 * abs(finals[False][1])
