@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ tc::P
         if (n < s.n_real) {
             const int u = s.n0 + n;
             if (s.type == tc::SRC_HID) {
-                v = p[s.w_off + (int64_t)u * s.ld + s.k0 + k];
+                v = p[s.w_off + (int64_t)u * s.ld + (s.k0 + k + s.k_rot) % s.ld];
             } else if (s.type == tc::SRC_BIAS) {
                 if (k < 2) { v = p[s.b_off + u]; lo = k == 1; }
             } else {  // SRC_L1: [W_hi | W_hi | W_lo (3 terms) | b_hi b_lo] against [in_hi | in_lo | in_hi | 1 1]

@@ -24,10 +24,12 @@
 //     column halves of a row meet in shared memory, where the row's owner picks net(obs) up.
 //
 // Layers (reference elegantrl/net_residual.py), Da = TMEM columns [0,H), Db = [H,2H):
-//   modular (:138-205): P0 other_net.0 -> Da, integrator_net.0 -> Db;  P1 other_net.2 -> Da[0:H/2] (behind the epilogue
-//                       of Da);  P2 integrator_net.2 -> Da[H/2:H] (behind the epilogue of Db);  P3 net.0 on
-//                       cat = Da -> Db;  net.2 in the epilogue of Db.
-//   plain (:6-66) / CriticAdv (net.py:274-277): P0 net.0 -> Da, P1 net.2 -> Db, P2 net.4 -> Da, net.6 in the epilogue of Da.
+//   modular (:138-205): P0 integrator_net.0 -> Da (issued while the previous pass finishes on Db), other_net.0 -> Db;
+//                       P1 integrator_net.2 -> Da[0:H/2] (behind the epilogue of Da);  P2 other_net.2 -> Da[H/2:H]
+//                       (behind the epilogue of Db);  P3 net.0 on cat' = Da = [integrator | other] -> Db (input columns
+//                       rotated in the pack);  net.2 in the epilogue of Db.
+//   plain (:6-66) / CriticAdv (net.py:274-277): P0 net.0 -> X, P1 net.2 -> Y, P2 net.4 -> X, net.6 in the epilogue of X,
+//                       with (X, Y) = (Da, Db) on even passes and (Db, Da) on odd ones, so that P0 never waits.
 #pragma once
 
 #include "pime_common.cuh"
@@ -78,6 +80,7 @@ struct BlkSrc {          // how pack_kernel fills the block from the fp32 state_
     int n0, n_real;      // first output unit of the block, number of real (non-padding) rows
     int k0;              // first K index (SRC_HID: input unit; SRC_L1: position in the split operand)
     int c0, cN;          // SRC_L1: the weight matrix covers inputs [c0, c0+cN) of the nin-wide input vector
+    int k_rot;           // SRC_HID: input unit k of the kernel is column (k + k_rot) % ld of the reference weight matrix
 };
 
 __host__ __device__ constexpr int geo_acols(int H) { return H < 64 ? 64 : H; }
@@ -101,6 +104,7 @@ struct PackLayout {
 struct GemmSpec {
     int type, N, n_real, K16, a_off, d_col, w_off, ld, b_off, c0, cN;
     uint32_t flags;        // extra flags for every block
+    int k_rot;
 };
 
 __host__ __device__ constexpr int blk_k16(int N, int K16) {   // K=16 slices per block: as many as fit 16 KB
@@ -125,7 +129,7 @@ inline bool emit_gemm(PackLayout &L, const GemmSpec &g) {
         s.type = g.type; s.w_off = g.w_off; s.ld = g.ld; s.b_off = g.b_off;
         s.n0 = 0;
         s.n_real = g.n_real;
-        s.k0 = k * 16; s.c0 = g.c0; s.cN = g.cN;
+        s.k0 = k * 16; s.c0 = g.c0; s.cN = g.cN; s.k_rot = g.k_rot;
         L.f16_bytes += g.N * kk * 32;
         ++L.nblk;
     }
@@ -144,13 +148,13 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
     const int Da = 0, Db = H;
     bool ok = true;
     auto bias = [&](int N, int n_real, int b_off, int d_col) {
-        ok = ok && emit_gemm(L, GemmSpec{SRC_BIAS, N, n_real, 1, a_ones, d_col, 0, 0, b_off, 0, 0, 0u});
+        ok = ok && emit_gemm(L, GemmSpec{SRC_BIAS, N, n_real, 1, a_ones, d_col, 0, 0, b_off, 0, 0, 0u, 0});
     };
-    auto hid = [&](int N, int n_real, int w_off, int d_col) {   // accumulates on top of the bias block
-        ok = ok && emit_gemm(L, GemmSpec{SRC_HID, N, n_real, HK, 0, d_col, w_off, H, 0, 0, 0, 0u});
+    auto hid = [&](int N, int n_real, int w_off, int d_col, int k_rot = 0) {   // accumulates on top of the bias block
+        ok = ok && emit_gemm(L, GemmSpec{SRC_HID, N, n_real, HK, 0, d_col, w_off, H, 0, 0, 0, 0u, k_rot});
     };
     auto l1 = [&](int N, int w_off, int ld, int b_off, int c0, int cN, int d_col) {
-        ok = ok && emit_gemm(L, GemmSpec{SRC_L1, N, N, L.KP / 16, a_obs, d_col, w_off, ld, b_off, c0, cN, BLK_OBS_A});
+        ok = ok && emit_gemm(L, GemmSpec{SRC_L1, N, N, L.KP / 16, a_obs, d_col, w_off, ld, b_off, c0, cN, BLK_OBS_A, 0});
     };
     if (c.kind == PIME_ACTOR_MODULAR) {
         const int So = S - D;
@@ -162,11 +166,14 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
         for (int j = 0; j < 12; ++j) { L.src[j] = o; o += sizes[j]; }
         L.param_count = o;
         L.nin = 4; L.nterms = 3; L.KP = 16;   // inputs (o0,o1,o2,I): 3 x 4 + 2 = 14 <= 16
-        l1(H, L.src[0], So, L.src[1], 0, So, Da);                          // P0 other_net.0 -> Da
-        l1(H, L.src[4], 1, L.src[5], 3, 1, Db);                            //    integrator_net.0 -> Db
-        bias(Hh, Hh, L.src[3], Da); hid(Hh, Hh, L.src[2], Da);             // P1 other_net.2 -> Da[0:H/2]
-        bias(Hh, Hh, L.src[7], Da + Hh); hid(Hh, Hh, L.src[6], Da + Hh);   // P2 integrator_net.2 -> Da[H/2:H]
-        bias(H, H, L.src[9], Db); hid(H, H, L.src[8], Db);                 // P3 net.0 -> Db
+        // The integrator branch runs first: its first layer goes to Da, which is free while the previous pass is still
+        // in its last epilogue (on Db), so a pass starts without waiting.  cat is therefore [integrator | other] and
+        // net.0's input columns are rotated by H/2 to match.
+        l1(H, L.src[4], 1, L.src[5], 3, 1, Da);                            // P0 integrator_net.0 -> Da
+        l1(H, L.src[0], So, L.src[1], 0, So, Db);                          //    other_net.0 -> Db
+        bias(Hh, Hh, L.src[7], Da); hid(Hh, Hh, L.src[6], Da);             // P1 integrator_net.2 -> Da[0:H/2]
+        bias(Hh, Hh, L.src[3], Da + Hh); hid(Hh, Hh, L.src[2], Da + Hh);   // P2 other_net.2 -> Da[H/2:H]
+        bias(H, H, L.src[9], Db); hid(H, H, L.src[8], Db, Hh);             // P3 net.0 on cat' = [integrator | other] -> Db
         L.out_w = L.src[10]; L.out_b = L.src[11];                          // net.2: fp32 dot product inside the last epilogue
     } else {
         // state_dict order: net.0.{w,b} net.2.{w,b} net.4.{w,b} net.6.{w,b}
@@ -369,7 +376,7 @@ template <int KIND, int H> struct Engine {
     using G = Geo<KIND, H>;
     uint8_t *sA, *sRing;
     const Blk *tbl;
-    uint64_t *full, *empty, *a_rdy, *a_free, *o_rdy, *d_ready, *out_rdy, *h_rdy;
+    uint64_t *full, *empty, *a_rdy, *a_free, *o_rdy, *d_ready, *out_rdy, *h_rdy, *l1b_rdy, *p0_rdy;
     float *sOutW, *sPart;
     uint32_t *tmem_slot;
     uint32_t tmem_base;
@@ -390,7 +397,9 @@ template <int KIND, int H> struct Engine {
         d_ready = o_rdy + 2;
         out_rdy = d_ready + 1;
         h_rdy = out_rdy + 1;
-        tmem_slot = reinterpret_cast<uint32_t *>(h_rdy + 1);
+        l1b_rdy = h_rdy + 1;
+        p0_rdy = l1b_rdy + 1;
+        tmem_slot = reinterpret_cast<uint32_t *>(p0_rdy + 1);
         sOutW = reinterpret_cast<float *>(smem + G::OutWOff);
         sPart = reinterpret_cast<float *>(smem + G::PartOff);
         const int tid = threadIdx.x;
@@ -402,6 +411,8 @@ template <int KIND, int H> struct Engine {
             mbar_init(d_ready, 1);
             mbar_init(out_rdy, kWorkerThreads);
             mbar_init(h_rdy, 1);
+            mbar_init(l1b_rdy, 1);
+            mbar_init(p0_rdy, 1);
             fence_barrier_init();
         }
         if (tid / 32 == kMmaWarp) tmem_alloc(tmem_slot, G::TmemCols);
@@ -519,28 +530,30 @@ template <int KIND, int H> struct Engine {
             mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);            // the group's observation operand is written
             tc_fence_after();
             if constexpr (G::kModular) {
-                blk<H, true>(obs, 1, Da);                              // P0: other_net.0 -> Da (Da was released by the third epilogue)
+                blk<H, true>(obs, 1, Da, p0_rdy);                      // P0: integrator_net.0 -> Da (free since the third epilogue);
+                                                                       // own barrier: it completes while the workers still wait on d_ready
                 if (q > 0) { mbar_wait(out_rdy, ((uint32_t)q - 1u) & 1u); tc_fence_after(); }   // last epilogue of the previous pass has read Db
-                blk<H, true>(obs, 1, Db, d_ready);                     //     integrator_net.0 -> Db
-                layer<Hh, true>(Da, apar, (Hh + 63) / 64, h_rdy, nullptr);     // P1: other_net.2 -> Da[0:H/2], behind the epilogue of Da
+                blk<H, true>(obs, 1, Db, l1b_rdy);                     //     other_net.0 -> Db
+                layer<Hh, true>(Da, apar, (Hh + 63) / 64, h_rdy, nullptr);     // P1: integrator_net.2 -> Da[0:H/2], behind the epilogue of Da
                 apar ^= 1;
-                layer<Hh, true>(Da + Hh, apar, 0, d_ready, nullptr);   // P2: integrator_net.2 -> Da[H/2:H], behind the epilogue of Db
+                layer<Hh, true>(Da + Hh, apar, 0, d_ready, nullptr);   // P2: other_net.2 -> Da[H/2:H], behind the epilogue of Db
                 apar ^= 1;
-                layer<H, false>(Db, apar, 0, d_ready, nullptr);        // P3: net.0 on cat -> Db; net.2 is the workers' dot product
+                layer<H, false>(Db, apar, 0, d_ready, nullptr);        // P3: net.0 on cat' -> Db; net.2 is the workers' dot product
                 apar ^= 1;
             } else {
-                if (q > 0) { mbar_wait(out_rdy, ((uint32_t)q - 1u) & 1u); tc_fence_after(); }   // last epilogue of the previous pass has read Da
-                const int K16 = mp.KP / 16;                            // P0: net.0 -> Da (first-layer operand K = KP)
+                const uint32_t X = (q & 1) ? Db : Da, Y = (q & 1) ? Da : Db;   // Y = the previous pass's X
+                const int K16 = mp.KP / 16;                            // P0: net.0 -> X (first-layer operand K = KP)
                 constexpr int kpb = blk_k16(H, 4);
                 for (int k = 0; k < K16; k += kpb) {
                     const int kk = K16 - k < kpb ? K16 - k : kpb;
-                    uint64_t *x = k + kpb >= K16 ? d_ready : nullptr;
-                    if (k == 0) blk<H, true>(obs, kk, Da, x);
-                    else blk<H, false>(obs + (uint32_t)k * kK16Bytes, kk, Da, x);
+                    uint64_t *x = k + kpb >= K16 ? p0_rdy : nullptr;
+                    if (k == 0) blk<H, true>(obs, kk, X, x);
+                    else blk<H, false>(obs + (uint32_t)k * kK16Bytes, kk, X, x);
                 }
-                layer<H, false>(Db, apar, 0, d_ready, nullptr);        // P1: net.2 -> Db
+                if (q > 0) { mbar_wait(out_rdy, ((uint32_t)q - 1u) & 1u); tc_fence_after(); }   // last epilogue of the previous pass has read Y
+                layer<H, false>(Y, apar, 0, d_ready, nullptr);         // P1: net.2 -> Y
                 apar ^= 1;
-                layer<H, false>(Da, apar, 0, d_ready, nullptr);        // P2: net.4 -> Da; net.6 is the workers' dot product
+                layer<H, false>(X, apar, 0, d_ready, nullptr);         // P2: net.4 -> X; net.6 is the workers' dot product
                 apar ^= 1;
             }
         }
@@ -621,23 +634,28 @@ template <int KIND, int H> struct Engine {
         };
         for (int q = 0; q < passes; ++q) {
             if constexpr (G::kModular) {
-                wait_d();                                             // P0: Da = other_net.0, Db = integrator_net.0 (net_residual.py:151,154)
-                epilogue<false>(row, half, 0, 0);                     // tanh(Da) -> A, feeds other_net.2 (:152)
-                epilogue<true>(row, half, H, 0u);                     // tanh(Db) -> A, feeds integrator_net.2 (:155)
-                mbar_wait(h_rdy, (uint32_t)q & 1u);                   // P1: Da[0:H/2] = other_net.2 (complete long ago)
+                mbar_wait(p0_rdy, (uint32_t)q & 1u);                  // P0: Da = integrator_net.0 (net_residual.py:154)
                 tc_fence_after();
-                epilogue<true, 0, G::NP / 2>(row, half, 0, 1u);       // first half of cat (:170) while integrator_net.2 finishes
-                wait_d();                                             // P2: Da[H/2:H] = integrator_net.2
+                epilogue<false>(row, half, 0, 0);                     // tanh(Da) -> A, feeds integrator_net.2 (:155)
+                mbar_wait(l1b_rdy, (uint32_t)q & 1u);                 //     Db = other_net.0 (:151)
+                tc_fence_after();
+                epilogue<true>(row, half, H, 0u);                     // tanh(Db) -> A, feeds other_net.2 (:152)
+                mbar_wait(h_rdy, (uint32_t)q & 1u);                   // P1: Da[0:H/2] = integrator_net.2 (complete long ago)
+                tc_fence_after();
+                epilogue<true, 0, G::NP / 2>(row, half, 0, 1u);       // first half of cat' (:170) while other_net.2 finishes
+                wait_d();                                             // P2: Da[H/2:H] = other_net.2
                 epilogue<true, G::NP / 2, G::NP>(row, half, 0, 1u);   // second half of cat, feeds net.0 (:157)
                 wait_d();                                             // P3: Db = net.0
                 epilogue_dot(row, half, H, q & 1);                    // net.2 (:158)
             } else {
+                const int X = (q & 1) ? H : 0, Y = (q & 1) ? 0 : H;
+                mbar_wait(p0_rdy, (uint32_t)q & 1u);
+                tc_fence_after();
+                epilogue<false>(row, half, X, 0);
                 wait_d();
-                epilogue<false>(row, half, 0, 0);
+                epilogue<false>(row, half, Y, 0);
                 wait_d();
-                epilogue<false>(row, half, H, 0);
-                wait_d();
-                epilogue_dot(row, half, 0, q & 1);
+                epilogue_dot(row, half, X, q & 1);
             }
         }
     }
