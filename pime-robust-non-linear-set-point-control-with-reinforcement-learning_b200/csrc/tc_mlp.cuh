@@ -51,7 +51,7 @@ constexpr int kMaxBlocks = 32;
 constexpr int kHeaderBytes = 2048;         // head of the pack: block list (kMaxBlocks x 16 B), then the fp32 output layer
 constexpr int kOutWOff = 512;              // fp32 [H] weight vector + bias of the last Linear(H -> 1), inside the header
 constexpr int kMaxKP = 64;                 // widest first-layer operand (2 x 31 inputs + 2)
-constexpr int kMaxChunks = 4;              // 64-column chunks of a layer (H <= 256): the granularity of the MMA pipelining
+constexpr int kMaxChunks = 8;              // 32-column pieces of a layer (H <= 256): the granularity of the MMA pipelining
 
 // ------------------------------------------------------------------------------------------------ block program
 enum : uint32_t {
@@ -211,9 +211,9 @@ inline MlpParams make_mlp_params(const PackLayout &L, const void *pack) {
 template <int KIND, int H> struct Geo {
     static constexpr bool kModular = KIND == PIME_ACTOR_MODULAR;
     static constexpr bool kRelu = KIND == PIME_CRITIC_ADV;
-    static constexpr int NP = H / 32;                        // 32-column pieces per layer (one worker epilogue step)
-    static constexpr int NCh = (H + 63) / 64;                // 64-column chunks per layer (MMA pipelining granularity)
-    static constexpr int ChunkArrivals = H >= 64 ? 2 * kRows : kRows;  // both halves write a piece of every chunk
+    static constexpr int NP = H / 32;                        // 32-column pieces per layer: one epilogue step (16 columns per
+                                                             // worker half) and the granularity of the MMA pipelining
+    static constexpr int ChunkArrivals = 2 * kRows;          // both halves write 16 columns of every piece
     static constexpr int ABytes = geo_abytes(H);
     static constexpr int ObsOff = geo_obs_off(H);
     static constexpr int ObsGroupBytes = geo_obs_group_bytes(KIND);
@@ -371,6 +371,16 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) 
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) {
+    uint32_t *u = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+          "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 template <int KIND, int H> struct Engine {
     using G = Geo<KIND, H>;
@@ -500,21 +510,20 @@ template <int KIND, int H> struct Engine {
         blk<N, true>((uint32_t)G::OnesOff, 1, d_col);
 #pragma unroll
         for (int k = 0; k < K16; k += kpb) {
-            const int c_hi = ((k + kpb) * 16 + 63) / 64;   // chunks touched by K columns [16k, 16(k+kpb))
+            const int c_hi = ((k + kpb) * 16 + 31) / 32;   // pieces touched by K columns [16k, 16(k+kpb))
             need(c_hi);
             const bool last = k + kpb >= K16;
-            uint64_t *f1 = nullptr, *f2 = nullptr;
-            if (FREE) {   // chunks completed by this block (kpb*16 is 32, 64 or a multiple of 64)
-                const int c_done_lo = (k * 16) / 64, c_done_hi = last ? G::NCh : ((k + kpb) * 16) / 64;
-                if (c_done_hi > c_done_lo) f1 = &a_free[c_done_lo];
-                if (c_done_hi > c_done_lo + 1) f2 = &a_free[c_done_lo + 1];
-                if (c_done_hi > c_done_lo + 2) {   // a block spanning 3+ chunks: commit the rest separately
-                    if (elect_one()) for (int c = c_done_lo + 2; c < c_done_hi; ++c) mma_commit(&a_free[c]);
+            if (FREE) {   // pieces completed by this block: release them once its MMAs have read the A operand
+                const int c_lo = (k * 16) / 32;
+                blk<N, false>((uint32_t)k * kK16Bytes, kpb, d_col, &a_free[c_lo], c_hi - c_lo > 1 ? &a_free[c_lo + 1] : nullptr,
+                              last ? e1 : nullptr);
+                if (c_hi - c_lo > 2) {   // a block spanning 3+ pieces (small N): release the rest, still after its MMAs
+                    if (elect_one()) for (int c = c_lo + 2; c < c_hi; ++c) mma_commit(&a_free[c]);
                     __syncwarp();
                 }
+            } else {
+                blk<N, false>((uint32_t)k * kK16Bytes, kpb, d_col, last ? e1 : nullptr, last ? e2 : nullptr);
             }
-            if (FREE) blk<N, false>((uint32_t)k * kK16Bytes, kpb, d_col, f1, f2, last ? e1 : nullptr);
-            else blk<N, false>((uint32_t)k * kK16Bytes, kpb, d_col, last ? e1 : nullptr, last ? e2 : nullptr);
         }
     }
 
@@ -534,7 +543,7 @@ template <int KIND, int H> struct Engine {
                                                                        // own barrier: it completes while the workers still wait on d_ready
                 if (q > 0) { mbar_wait(out_rdy, ((uint32_t)q - 1u) & 1u); tc_fence_after(); }   // last epilogue of the previous pass has read Db
                 blk<H, true>(obs, 1, Db, l1b_rdy);                     //     other_net.0 -> Db
-                layer<Hh, true>(Da, apar, (Hh + 63) / 64, h_rdy, nullptr);     // P1: integrator_net.2 -> Da[0:H/2], behind the epilogue of Da
+                layer<Hh, true>(Da, apar, (Hh + 31) / 32, h_rdy, nullptr);     // P1: integrator_net.2 -> Da[0:H/2], behind the epilogue of Da
                 apar ^= 1;
                 layer<Hh, true>(Da + Hh, apar, 0, d_ready, nullptr);   // P2: other_net.2 -> Da[H/2:H], behind the epilogue of Db
                 apar ^= 1;
@@ -559,64 +568,58 @@ template <int KIND, int H> struct Engine {
         }
     }
 
-    // ---- workers (warps 0-7): thread (row, half) runs the epilogue of the even (half 0) / odd (half 1) chunks
+    // ---- workers (warps 0-7): thread (row, half) runs the epilogue of columns [16 half, 16 half + 16) of every piece
     __device__ __forceinline__ void a_store8(int row, int kchunk, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3) {
         *reinterpret_cast<uint4 *>(sA + (size_t)kchunk * kChunkBytes + row * 16) = make_uint4(p0, p1, p2, p3);
     }
-    // A[:, 32j .. 32j+32) = act(D[:, dcol + 32j ..)) for the 32-column pieces j of this half (even / odd); the bias
-    // is already in D.  Piece j belongs to chunk j/2, whose barrier collects both halves.
-    // WAIT_FREE: the previous reader of the A chunk may still be in flight (no d_ready wait in between): wait a_free
-    // (a_free[c] completes twice per pass: other_net.2 and integrator_net.2 each release chunk c once they have read it).
+    // A[:, c] = act(D[:, dcol + c]) for this thread's 16 columns [32j + 16 half, +16) of every piece j in [JB, JE); the
+    // bias is already in D.  Both halves arrive on the piece's barrier, so pieces complete one after the other and the
+    // MMAs of the next layer follow one piece behind.
+    // WAIT_FREE: the previous reader of the A piece may still be in flight (no d_ready wait in between): wait a_free
+    // (a_free[j] completes twice per pass: integrator_net.2 and other_net.2 each release piece j once they have read it).
     template <bool WAIT_FREE, int JB = 0, int JE = G::NP>
     __device__ __forceinline__ void epilogue(int row, int half, int dcol, uint32_t free_parity) {
-        const uint32_t taddr = tmem_base + ((uint32_t)((row / 32) * 32) << 16) + (uint32_t)dcol;
-        float v[2][32];
-        const int j0 = JB + ((half - JB) & 1);   // first piece of this half inside [JB, JE)
-        if (j0 < JE) tmem_ld32_issue(taddr + j0 * 32, v[0]);
+        const uint32_t taddr = tmem_base + ((uint32_t)((row / 32) * 32) << 16) + (uint32_t)(dcol + 16 * half);
+        float v[2][16];
+        if (JB < JE) tmem_ld16_issue(taddr + JB * 32, v[0]);
 #pragma unroll
-        for (int it = 0; it < (JE - JB + 1) / 2; ++it) {
-            const int j = j0 + 2 * it;
-            if (j < JE) {
-                tmem_wait_ld();
-                if (j + 2 < JE) tmem_ld32_issue(taddr + (j + 2) * 32, v[(it + 1) & 1]);
-                float(&x)[32] = v[it & 1];
+        for (int j = JB; j < JE; ++j) {
+            tmem_wait_ld();
+            if (j + 1 < JE) tmem_ld16_issue(taddr + (j + 1) * 32, v[(j - JB + 1) & 1]);
+            float(&x)[16] = v[(j - JB) & 1];
 #pragma unroll
-                for (int e = 0; e < 32; ++e) x[e] = act_fn<G::kRelu>(x[e]);
-                if (WAIT_FREE) mbar_wait(&a_free[j >> 1], free_parity);
+            for (int e = 0; e < 16; ++e) x[e] = act_fn<G::kRelu>(x[e]);
+            if (WAIT_FREE) mbar_wait(&a_free[j], free_parity);
 #pragma unroll
-                for (int qd = 0; qd < 4; ++qd)
-                    a_store8(row, j * 4 + qd, pack_h2(x[qd * 8 + 0], x[qd * 8 + 1]), pack_h2(x[qd * 8 + 2], x[qd * 8 + 3]),
-                             pack_h2(x[qd * 8 + 4], x[qd * 8 + 5]), pack_h2(x[qd * 8 + 6], x[qd * 8 + 7]));
-                tc_fence_before();
-                fence_proxy_async();
-                mbar_arrive(&a_rdy[j >> 1]);
-            }
+            for (int qd = 0; qd < 2; ++qd)
+                a_store8(row, j * 4 + 2 * half + qd, pack_h2(x[qd * 8 + 0], x[qd * 8 + 1]), pack_h2(x[qd * 8 + 2], x[qd * 8 + 3]),
+                         pack_h2(x[qd * 8 + 4], x[qd * 8 + 5]), pack_h2(x[qd * 8 + 6], x[qd * 8 + 7]));
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(&a_rdy[j]);
         }
     }
 
-    // Last layer: partial dot product of this half's pieces, sum_c act(D[:, c]) * w_out[c] in fp32; the two halves of
+    // Last layer: partial dot product over this thread's columns, sum_c act(D[:, c]) * w_out[c] in fp32; the two halves of
     // a row meet in sPart[g][half][row], out_rdy collects all 256 workers (and tells the MMA warp that D is free again).
     __device__ __forceinline__ void epilogue_dot(int row, int half, int dcol, int g) {
-        const uint32_t taddr = tmem_base + ((uint32_t)((row / 32) * 32) << 16) + (uint32_t)dcol;
-        float v[2][32];
+        const uint32_t taddr = tmem_base + ((uint32_t)((row / 32) * 32) << 16) + (uint32_t)(dcol + 16 * half);
+        float v[2][16];
         float acc0 = 0.0f, acc1 = 0.0f;
-        if (half < G::NP) tmem_ld32_issue(taddr + half * 32, v[0]);
+        tmem_ld16_issue(taddr, v[0]);
 #pragma unroll
-        for (int it = 0; it < (G::NP + 1) / 2; ++it) {
-            const int j = half + 2 * it;
-            if (j < G::NP) {
-                tmem_wait_ld();
-                if (j + 2 < G::NP) tmem_ld32_issue(taddr + (j + 2) * 32, v[(it + 1) & 1]);
-                float(&x)[32] = v[it & 1];
-                const float4 *w = reinterpret_cast<const float4 *>(sOutW + j * 32);
+        for (int j = 0; j < G::NP; ++j) {
+            tmem_wait_ld();
+            if (j + 1 < G::NP) tmem_ld16_issue(taddr + (j + 1) * 32, v[(j + 1) & 1]);
+            float(&x)[16] = v[j & 1];
+            const float4 *w = reinterpret_cast<const float4 *>(sOutW + j * 32 + 16 * half);
 #pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                    const float4 ww = w[e / 4];
-                    acc0 = fmaf(act_fn<G::kRelu>(x[e + 0]), ww.x, acc0);
-                    acc1 = fmaf(act_fn<G::kRelu>(x[e + 1]), ww.y, acc1);
-                    acc0 = fmaf(act_fn<G::kRelu>(x[e + 2]), ww.z, acc0);
-                    acc1 = fmaf(act_fn<G::kRelu>(x[e + 3]), ww.w, acc1);
-                }
+            for (int e = 0; e < 16; e += 4) {
+                const float4 ww = w[e / 4];
+                acc0 = fmaf(act_fn<G::kRelu>(x[e + 0]), ww.x, acc0);
+                acc1 = fmaf(act_fn<G::kRelu>(x[e + 1]), ww.y, acc1);
+                acc0 = fmaf(act_fn<G::kRelu>(x[e + 2]), ww.z, acc0);
+                acc1 = fmaf(act_fn<G::kRelu>(x[e + 3]), ww.w, acc1);
             }
         }
         sPart[(g * 2 + half) * kRows + row] = acc0 + acc1;
