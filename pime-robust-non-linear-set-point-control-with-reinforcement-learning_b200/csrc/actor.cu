@@ -12,6 +12,10 @@ __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ tc::P
         float *ow = reinterpret_cast<float *>(out + tc::kOutWOff);
         for (int j = threadIdx.x; j < L.H; j += blockDim.x) ow[j] = p[L.out_w + j];
         if (threadIdx.x == 0) ow[L.H] = p[L.out_b];
+        if (L.kind == PIME_ACTOR_MODULAR) {   // integrator_net.0 (one input): interleaved (w, b) pairs, fp32
+            float *wb = reinterpret_cast<float *>(out + tc::kL1iOff);
+            for (int j = threadIdx.x; j < L.H; j += blockDim.x) { wb[2 * j] = p[L.l1i_w + j]; wb[2 * j + 1] = p[L.l1i_b + j]; }
+        }
         return;
     }
     const tc::Blk B = L.blk[b];

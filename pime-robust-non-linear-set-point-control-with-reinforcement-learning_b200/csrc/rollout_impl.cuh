@@ -243,9 +243,9 @@ template <typename Plant> struct Stepper {
 template <typename Plant, int KIND, int H>
 __global__ void __launch_bounds__(tc::kThreads, 1) rollout_kernel(Plant plant, tc::MlpParams mp, RolloutParams rp) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ double red[6][4];
     tc::Engine<KIND, H> eng;
     eng.setup(smem, mp);
+    double (*red)[4] = eng.red();
     const int tid = threadIdx.x, warp = tid >> 5;
     const int passes = 2 * rp.T;
     bool fault = false;

@@ -47,9 +47,10 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxBlkBytes = 16384;
 constexpr int kChunkBytes = kRows * 16;    // one K core-matrix column (8 fp16) for all 128 rows = 2048 B
 constexpr int kK16Bytes = 2 * kChunkBytes; // one K=16 slice of an A operand = 4096 B
-constexpr int kMaxBlocks = 32;
-constexpr int kHeaderBytes = 2048;         // head of the pack: block list (kMaxBlocks x 16 B), then the fp32 output layer
+constexpr int kMaxBlocks = 24;
+constexpr int kHeaderBytes = 4096;         // head of the pack: block list (kMaxBlocks x 16 B), then the fp32 layers
 constexpr int kOutWOff = 512;              // fp32 [H] weight vector + bias of the last Linear(H -> 1), inside the header
+constexpr int kL1iOff = 1600;              // modular: fp32 (w, b)[H] of integrator_net.0 (one input: runs on the CUDA cores)
 constexpr int kMaxKP = 64;                 // widest first-layer operand (2 x 31 inputs + 2)
 constexpr int kMaxChunks = 8;              // 32-column pieces of a layer (H <= 256): the granularity of the MMA pipelining
 
@@ -85,9 +86,10 @@ struct BlkSrc {          // how pack_kernel fills the block from the fp32 state_
 
 __host__ __device__ constexpr int geo_acols(int H) { return H < 64 ? 64 : H; }
 __host__ __device__ constexpr int geo_abytes(int H) { return kRows * geo_acols(H) * 2; }
+__host__ __device__ constexpr int geo_abufs(int kind) { return kind == PIME_ACTOR_MODULAR ? 2 : 1; }   // modular: double-buffered A tile
 __host__ __device__ constexpr int geo_obs_group_bytes(int kind) { return kind == PIME_ACTOR_MODULAR ? kK16Bytes : kRows * kMaxKP * 2; }
-__host__ __device__ constexpr int geo_obs_off(int H) { return geo_abytes(H); }
-__host__ __device__ constexpr int geo_ones_off(int kind, int H) { return geo_abytes(H) + 2 * geo_obs_group_bytes(kind); }
+__host__ __device__ constexpr int geo_obs_off(int kind, int H) { return geo_abufs(kind) * geo_abytes(H); }
+__host__ __device__ constexpr int geo_ones_off(int kind, int H) { return geo_obs_off(kind, H) + 2 * geo_obs_group_bytes(kind); }
 
 struct PackLayout {
     int kind, H, S, D;
@@ -97,6 +99,7 @@ struct PackLayout {
     int f16_bytes, total_bytes;
     int src[12];           // offsets of the state_dict tensors inside `params`
     int out_w, out_b;      // offsets of the last layer's weight vector / bias inside `params`
+    int l1i_w, l1i_b;      // modular: offsets of integrator_net.0's weight / bias inside `params`
     Blk blk[kMaxBlocks];
     BlkSrc bsrc[kMaxBlocks];
 };
@@ -105,6 +108,7 @@ struct GemmSpec {
     int type, N, n_real, K16, a_off, d_col, w_off, ld, b_off, c0, cN;
     uint32_t flags;        // extra flags for every block
     int k_rot;
+    int k16_lo, k16_hi;    // K range (in K=16 slices) emitted by this call; k16_hi = 0: all
 };
 
 __host__ __device__ constexpr int blk_k16(int N, int K16) {   // K=16 slices per block: as many as fit 16 KB
@@ -114,8 +118,9 @@ __host__ __device__ constexpr int blk_k16(int N, int K16) {   // K=16 slices per
 inline bool emit_gemm(PackLayout &L, const GemmSpec &g) {
     const int kpb = blk_k16(g.N, g.K16);
     if (g.N > 256 || g.N % 16 || kpb < 1) return false;
-    for (int k = 0; k < g.K16; k += kpb) {
-        const int kk = g.K16 - k < kpb ? g.K16 - k : kpb;
+    const int k_lo = g.k16_lo, k_hi = g.k16_hi ? g.k16_hi : g.K16;
+    for (int k = k_lo; k < k_hi; k += kpb) {
+        const int kk = k_hi - k < kpb ? k_hi - k : kpb;
         if (L.nblk >= kMaxBlocks) return false;
         Blk &b = L.blk[L.nblk];
         BlkSrc &s = L.bsrc[L.nblk];
@@ -136,6 +141,12 @@ inline bool emit_gemm(PackLayout &L, const GemmSpec &g) {
     return true;
 }
 
+// K=16 slice at which the MMA program of integrator_net.2 is interrupted to issue other_net.0 (see Engine::mma_loop)
+__host__ __device__ constexpr int p1_split_k16(int H) {
+    const int K16 = H / 16, kpb = blk_k16(H / 2, K16);
+    return ((K16 / 2) / kpb) * kpb;
+}
+
 inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
     const int H = c.mid_dim, S = c.state_dim, D = c.integrator_dim;
     if (!(H == 32 || H == 64 || H == 128 || H == 256)) return false;
@@ -144,17 +155,17 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
     L = PackLayout{};
     L.kind = c.kind; L.H = H; L.S = S; L.D = D;
     const int Hh = H / 2, HK = H / 16;
-    const int a_obs = geo_obs_off(H), a_ones = geo_ones_off(c.kind, H);
+    const int a_obs = geo_obs_off(c.kind, H), a_ones = geo_ones_off(c.kind, H);
     const int Da = 0, Db = H;
     bool ok = true;
     auto bias = [&](int N, int n_real, int b_off, int d_col) {
-        ok = ok && emit_gemm(L, GemmSpec{SRC_BIAS, N, n_real, 1, a_ones, d_col, 0, 0, b_off, 0, 0, 0u, 0});
+        ok = ok && emit_gemm(L, GemmSpec{SRC_BIAS, N, n_real, 1, a_ones, d_col, 0, 0, b_off, 0, 0, 0u, 0, 0, 0});
     };
-    auto hid = [&](int N, int n_real, int w_off, int d_col, int k_rot = 0) {   // accumulates on top of the bias block
-        ok = ok && emit_gemm(L, GemmSpec{SRC_HID, N, n_real, HK, 0, d_col, w_off, H, 0, 0, 0, 0u, k_rot});
+    auto hid = [&](int N, int n_real, int w_off, int d_col, int k_rot = 0, int k_lo = 0, int k_hi = 0) {   // on top of the bias block
+        ok = ok && emit_gemm(L, GemmSpec{SRC_HID, N, n_real, HK, 0, d_col, w_off, H, 0, 0, 0, 0u, k_rot, k_lo, k_hi});
     };
     auto l1 = [&](int N, int w_off, int ld, int b_off, int c0, int cN, int d_col) {
-        ok = ok && emit_gemm(L, GemmSpec{SRC_L1, N, N, L.KP / 16, a_obs, d_col, w_off, ld, b_off, c0, cN, BLK_OBS_A, 0});
+        ok = ok && emit_gemm(L, GemmSpec{SRC_L1, N, N, L.KP / 16, a_obs, d_col, w_off, ld, b_off, c0, cN, BLK_OBS_A, 0, 0, 0});
     };
     if (c.kind == PIME_ACTOR_MODULAR) {
         const int So = S - D;
@@ -166,12 +177,16 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
         for (int j = 0; j < 12; ++j) { L.src[j] = o; o += sizes[j]; }
         L.param_count = o;
         L.nin = 4; L.nterms = 3; L.KP = 16;   // inputs (o0,o1,o2,I): 3 x 4 + 2 = 14 <= 16
-        // The integrator branch runs first: its first layer goes to Da, which is free while the previous pass is still
-        // in its last epilogue (on Db), so a pass starts without waiting.  cat is therefore [integrator | other] and
-        // net.0's input columns are rotated by H/2 to match.
-        l1(H, L.src[4], 1, L.src[5], 3, 1, Da);                            // P0 integrator_net.0 -> Da
+        // The integrator branch runs first and its one-input first layer runs on the CUDA cores (header, kL1iOff), so a
+        // pass can start while the previous one still owns both TMEM buffers.  cat is therefore [integrator | other]
+        // and net.0's input columns are rotated by H/2 to match.  other_net.0 is issued in the middle of
+        // integrator_net.2's K loop (p1_split_k16), right after the previous pass has released Db.
+        const int ks = p1_split_k16(H);
+        L.l1i_w = L.src[4]; L.l1i_b = L.src[5];
+        bias(Hh, Hh, L.src[7], Da);                                        // P1 integrator_net.2 -> Da[0:H/2]
+        if (ks > 0) hid(Hh, Hh, L.src[6], Da, 0, 0, ks);                   //    first K part
         l1(H, L.src[0], So, L.src[1], 0, So, Db);                          //    other_net.0 -> Db
-        bias(Hh, Hh, L.src[7], Da); hid(Hh, Hh, L.src[6], Da);             // P1 integrator_net.2 -> Da[0:H/2]
+        if (ks < HK) hid(Hh, Hh, L.src[6], Da, 0, ks, HK);                 //    integrator_net.2, second K part
         bias(Hh, Hh, L.src[3], Da + Hh); hid(Hh, Hh, L.src[2], Da + Hh);   // P2 other_net.2 -> Da[H/2:H]
         bias(H, H, L.src[9], Db); hid(H, H, L.src[8], Db, Hh);             // P3 net.0 on cat' = [integrator | other] -> Db
         L.out_w = L.src[10]; L.out_b = L.src[11];                          // net.2: fp32 dot product inside the last epilogue
@@ -215,17 +230,22 @@ template <int KIND, int H> struct Geo {
                                                              // worker half) and the granularity of the MMA pipelining
     static constexpr int ChunkArrivals = 2 * kRows;          // both halves write 16 columns of every piece
     static constexpr int ABytes = geo_abytes(H);
-    static constexpr int ObsOff = geo_obs_off(H);
+    static constexpr int ABufs = geo_abufs(KIND);
+    static constexpr int ObsOff = geo_obs_off(KIND, H);
     static constexpr int ObsGroupBytes = geo_obs_group_bytes(KIND);
     static constexpr int OnesOff = geo_ones_off(KIND, H);
     static constexpr int RingOff = OnesOff + kK16Bytes;
-    static constexpr int Stages = kModular ? 8 : 7;
+    static constexpr int Stages = kModular ? 5 : 7;
     static constexpr int TblOff = RingOff + Stages * kMaxBlkBytes;
     static constexpr int OutWOff = TblOff + kMaxBlocks * 16;          // fp32 [H] + bias of the output layer
     static constexpr int PartOff = OutWOff + (H + 4) * 4;              // fp32 [2 groups][2 halves][128 rows] partial dot products
-    static constexpr int BarOff = PartOff + 4 * kRows * 4;
+    static constexpr int L1iOff = PartOff + 4 * kRows * 4;             // modular: fp32 (w, b)[H] of integrator_net.0
+    static constexpr int SIOff = L1iOff + (kModular ? 2 * H * 4 : 0);  // modular: fp32 integrated error [2 groups][128 rows]
+    static constexpr int BarOff = SIOff + (kModular ? 2 * kRows * 4 : 0);
+    static constexpr int RedOff = BarOff + 320;                        // double[6][4] scratch of the statistics reduction
     static constexpr int SmemBytes = BarOff + 512;
     static constexpr int TmemCols = 2 * H < 32 ? 32 : 2 * H;
+    static_assert(SmemBytes <= 232448, "shared memory budget of one CTA");
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -386,14 +406,14 @@ template <int KIND, int H> struct Engine {
     using G = Geo<KIND, H>;
     uint8_t *sA, *sRing;
     const Blk *tbl;
-    uint64_t *full, *empty, *a_rdy, *a_free, *o_rdy, *d_ready, *out_rdy, *h_rdy, *l1b_rdy, *p0_rdy;
-    float *sOutW, *sPart;
+    uint64_t *full, *empty, *a_rdy, *o_rdy, *d_ready, *out_rdy, *h_rdy, *l1b_rdy, *p0_rdy;
+    float *sOutW, *sPart, *sL1i, *sI;
     uint32_t *tmem_slot;
     uint32_t tmem_base;
     MlpParams mp;
 
-    // All kThreads threads.  Carves shared memory, initialises barriers, allocates TMEM, loads the block program and
-    // writes the constant "ones" operand.
+    // All kThreads threads.  Carves shared memory, initialises barriers, allocates TMEM, loads the block list and the
+    // fp32 layers, writes the constant "ones" operand.
     __device__ __forceinline__ void setup(uint8_t *smem, const MlpParams &p) {
         mp = p;
         sA = smem;
@@ -402,8 +422,7 @@ template <int KIND, int H> struct Engine {
         full = reinterpret_cast<uint64_t *>(smem + G::BarOff);
         empty = full + kMaxStages;
         a_rdy = empty + kMaxStages;
-        a_free = a_rdy + kMaxChunks;
-        o_rdy = a_free + kMaxChunks;
+        o_rdy = a_rdy + 2 * kMaxChunks;   // one set of piece barriers per A tile
         d_ready = o_rdy + 2;
         out_rdy = d_ready + 1;
         h_rdy = out_rdy + 1;
@@ -412,10 +431,12 @@ template <int KIND, int H> struct Engine {
         tmem_slot = reinterpret_cast<uint32_t *>(p0_rdy + 1);
         sOutW = reinterpret_cast<float *>(smem + G::OutWOff);
         sPart = reinterpret_cast<float *>(smem + G::PartOff);
+        sL1i = reinterpret_cast<float *>(smem + G::L1iOff);
+        sI = reinterpret_cast<float *>(smem + G::SIOff);
         const int tid = threadIdx.x;
         if (tid == 0) {
             for (int s = 0; s < G::Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-            for (int j = 0; j < kMaxChunks; ++j) { mbar_init(&a_rdy[j], G::ChunkArrivals); mbar_init(&a_free[j], 1); }
+            for (int j = 0; j < 2 * kMaxChunks; ++j) mbar_init(&a_rdy[j], G::ChunkArrivals);
             mbar_init(&o_rdy[0], kOwnerThreads);
             mbar_init(&o_rdy[1], kOwnerThreads);
             mbar_init(d_ready, 1);
@@ -430,6 +451,8 @@ template <int KIND, int H> struct Engine {
         uint4 *dst = reinterpret_cast<uint4 *>(smem + G::TblOff);
         for (int j = tid; j < mp.nblk; j += kThreads) dst[j] = __ldg(src + j);
         for (int j = tid; j < H + 1; j += kThreads) sOutW[j] = __ldg(reinterpret_cast<const float *>(mp.pack + kOutWOff) + j);
+        if constexpr (G::kModular)
+            for (int j = tid; j < 2 * H; j += kThreads) sL1i[j] = __ldg(reinterpret_cast<const float *>(mp.pack + kL1iOff) + j);
         // ones operand: K=16 slice whose first two columns are 1.0 (fp16 0x3C00): multiplies [b_hi b_lo 0 ...]
         for (int j = tid; j < 2 * kRows; j += kThreads)
             *reinterpret_cast<uint4 *>(smem + G::OnesOff + j * 16) = j < kRows ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
@@ -439,6 +462,8 @@ template <int KIND, int H> struct Engine {
         tc_fence_after();
         tmem_base = *tmem_slot;
     }
+
+    __device__ __forceinline__ double (*red())[4] { return reinterpret_cast<double (*)[4]>(sA + G::RedOff); }
 
     __device__ __forceinline__ void teardown() {
         tc_fence_before();
@@ -468,11 +493,10 @@ template <int KIND, int H> struct Engine {
     // the order the producer streams.  Everything but the ring stage is a compile-time constant, so a block costs a
     // barrier poll, the tcgen05.mma instructions and one commit.
     uint32_t m_st, m_ph;     // ring stage / parity (MMA warp)
-    uint64_t adesc_base;     // descriptor of the operand area start (A tile, observation and ones operands share LBO/SBO)
+    uint64_t adesc_base;     // descriptor of the operand area start (A tiles, observation and ones operands share LBO/SBO)
 
     template <int N, bool FRESH>
-    __device__ __forceinline__ void blk(uint32_t a_off, int k16s, uint32_t d_col, uint64_t *x1 = nullptr, uint64_t *x2 = nullptr,
-                                        uint64_t *x3 = nullptr) {
+    __device__ __forceinline__ void blk(uint32_t a_off, int k16s, uint32_t d_col, uint64_t *x1 = nullptr, uint64_t *x2 = nullptr) {
         mbar_wait(&full[m_st], m_ph);
         tc_fence_after();
         if (elect_one()) {
@@ -487,43 +511,35 @@ template <int KIND, int H> struct Engine {
             mma_commit(&empty[m_st]);  // frees the ring slot once these MMAs have read it
             if (x1) mma_commit(x1);
             if (x2) mma_commit(x2);
-            if (x3) mma_commit(x3);
         }
         __syncwarp();
         if (++m_st == (uint32_t)G::Stages) { m_st = 0; m_ph ^= 1; }
     }
 
-    // One hidden layer: bias block (waits for the first `lag` chunks when the accumulator aliases columns that the
-    // feeding epilogue is still reading), then the weight blocks, each as soon as the A chunks it reads are written.
-    // FREE: release each A chunk (a_free) as soon as its last reader is issued.  e1/e2: barriers committed with the last block.
-    template <int N, bool FREE>
-    __device__ __forceinline__ void layer(uint32_t d_col, uint32_t apar, int lag, uint64_t *e1, uint64_t *e2) {
+    // K slices [K_LO, K_HI) of one hidden layer: (bias block first when BIAS, after waiting for the first `lag`
+    // pieces when the accumulator aliases columns the feeding epilogue is still reading), then the weight blocks, each
+    // as soon as the A pieces it reads are written.  abuf: which A tile the feeding epilogue writes.  e1/e2: barriers
+    // committed with the last block of the range.
+    template <int N, int K_LO = 0, int K_HI = H / 16, bool BIAS = true>
+    __device__ __forceinline__ void layer(uint32_t d_col, uint32_t apar, uint32_t abuf, int lag, uint64_t *e1, uint64_t *e2) {
         constexpr int K16 = H / 16, kpb = blk_k16(N, K16);
-        int waited = 0;
-        auto need = [&](int upto) {   // chunks [0, upto) of the feeding epilogue are in shared memory
+        const uint32_t a_tile = abuf * (uint32_t)G::ABytes;
+        int waited = (K_LO * 16) / 32;   // pieces below K_LO were waited on by the call that issued them
+        auto need = [&](int upto) {      // pieces [0, upto) of the feeding epilogue are in shared memory
             if (waited < upto) {
-                for (; waited < upto; ++waited) mbar_wait(&a_rdy[waited], apar);
+                for (; waited < upto; ++waited) mbar_wait(&a_rdy[abuf * kMaxChunks + waited], apar);
                 tc_fence_after();
             }
         };
-        need(lag);
-        blk<N, true>((uint32_t)G::OnesOff, 1, d_col);
+        if (BIAS) {
+            need(lag);
+            blk<N, true>((uint32_t)G::OnesOff, 1, d_col);
+        }
 #pragma unroll
-        for (int k = 0; k < K16; k += kpb) {
-            const int c_hi = ((k + kpb) * 16 + 31) / 32;   // pieces touched by K columns [16k, 16(k+kpb))
-            need(c_hi);
-            const bool last = k + kpb >= K16;
-            if (FREE) {   // pieces completed by this block: release them once its MMAs have read the A operand
-                const int c_lo = (k * 16) / 32;
-                blk<N, false>((uint32_t)k * kK16Bytes, kpb, d_col, &a_free[c_lo], c_hi - c_lo > 1 ? &a_free[c_lo + 1] : nullptr,
-                              last ? e1 : nullptr);
-                if (c_hi - c_lo > 2) {   // a block spanning 3+ pieces (small N): release the rest, still after its MMAs
-                    if (elect_one()) for (int c = c_lo + 2; c < c_hi; ++c) mma_commit(&a_free[c]);
-                    __syncwarp();
-                }
-            } else {
-                blk<N, false>((uint32_t)k * kK16Bytes, kpb, d_col, last ? e1 : nullptr, last ? e2 : nullptr);
-            }
+        for (int k = K_LO; k < K_HI; k += kpb) {
+            need(((k + kpb) * 16 + 31) / 32);   // pieces touched by K columns [16k, 16(k+kpb))
+            const bool last = k + kpb >= K_HI;
+            blk<N, false>(a_tile + (uint32_t)k * kK16Bytes, kpb, d_col, last ? e1 : nullptr, last ? e2 : nullptr);
         }
     }
 
@@ -532,25 +548,32 @@ template <int KIND, int H> struct Engine {
         constexpr uint32_t Da = 0, Db = H;
         m_st = 0; m_ph = 0;
         adesc_base = make_desc(smem_u32(sA), kChunkBytes, 128);
-        uint32_t apar = 0;   // parity of the next completion of the chunk barriers (every chunk completes once per epilogue)
+        uint32_t apar = 0;   // parity of the next completion of the piece barriers (every piece completes once per epilogue)
+        uint32_t ep = 0;     // modular: running count of A-writing epilogues: A tile and piece-barrier set = ep & 1, barrier
+                             // parity = (ep >> 1) & 1.  Alternating sets make it impossible for the workers to lap the MMA warp:
+                             // an epilogue reuses a set only after a wait that implies its previous phase was consumed.
         for (int q = 0; q < passes; ++q) {
             const uint32_t g = (uint32_t)q & 1u;
             const uint32_t obs = (uint32_t)G::ObsOff + g * (uint32_t)G::ObsGroupBytes;
-            mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);            // the group's observation operand is written
-            tc_fence_after();
             if constexpr (G::kModular) {
-                blk<H, true>(obs, 1, Da, p0_rdy);                      // P0: integrator_net.0 -> Da (free since the third epilogue);
-                                                                       // own barrier: it completes while the workers still wait on d_ready
-                if (q > 0) { mbar_wait(out_rdy, ((uint32_t)q - 1u) & 1u); tc_fence_after(); }   // last epilogue of the previous pass has read Db
-                blk<H, true>(obs, 1, Db, l1b_rdy);                     //     other_net.0 -> Db
-                layer<Hh, true>(Da, apar, (Hh + 31) / 32, h_rdy, nullptr);     // P1: integrator_net.2 -> Da[0:H/2], behind the epilogue of Da
-                apar ^= 1;
-                layer<Hh, true>(Da + Hh, apar, 0, d_ready, nullptr);   // P2: other_net.2 -> Da[H/2:H], behind the epilogue of Db
-                apar ^= 1;
-                layer<H, false>(Db, apar, 0, d_ready, nullptr);        // P3: net.0 on cat' -> Db; net.2 is the workers' dot product
-                apar ^= 1;
+                constexpr int KS = p1_split_k16(H);
+                // P1: integrator_net.2 -> Da[0:H/2] behind the CUDA-core epilogue of integrator_net.0.  Da is free: the
+                // third epilogue of the previous pass was consumed piece by piece by its net.0 MMAs (program order).
+                layer<Hh, 0, KS, true>(Da, (ep >> 1) & 1u, ep & 1u, 0, nullptr, nullptr);   // bias block + K slices below the split
+                mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);            // the group's observation operand is written
+                if (q > 0) mbar_wait(out_rdy, ((uint32_t)q - 1u) & 1u);    // last epilogue of the previous pass has read Db
+                tc_fence_after();
+                blk<H, true>(obs, 1, Db, l1b_rdy);                         // other_net.0 -> Db, in the shadow of the epilogue above
+                layer<Hh, KS, H / 16, false>(Da, (ep >> 1) & 1u, ep & 1u, 0, h_rdy, nullptr);
+                ++ep;
+                layer<Hh>(Da + Hh, (ep >> 1) & 1u, ep & 1u, 0, d_ready, nullptr);   // P2: other_net.2 -> Da[H/2:H], behind the epilogue of Db
+                ++ep;
+                layer<H>(Db, (ep >> 1) & 1u, ep & 1u, 0, d_ready, nullptr);         // P3: net.0 on cat' -> Db; net.2 is the workers' dot product
+                ++ep;
             } else {
                 const uint32_t X = (q & 1) ? Db : Da, Y = (q & 1) ? Da : Db;   // Y = the previous pass's X
+                mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);
+                tc_fence_after();
                 const int K16 = mp.KP / 16;                            // P0: net.0 -> X (first-layer operand K = KP)
                 constexpr int kpb = blk_k16(H, 4);
                 for (int k = 0; k < K16; k += kpb) {
@@ -560,25 +583,32 @@ template <int KIND, int H> struct Engine {
                     else blk<H, false>(obs + (uint32_t)k * kK16Bytes, kk, X, x);
                 }
                 if (q > 0) { mbar_wait(out_rdy, ((uint32_t)q - 1u) & 1u); tc_fence_after(); }   // last epilogue of the previous pass has read Y
-                layer<H, false>(Y, apar, 0, d_ready, nullptr);         // P1: net.2 -> Y
+                layer<H>(Y, apar, 0u, 0, d_ready, nullptr);            // P1: net.2 -> Y
                 apar ^= 1;
-                layer<H, false>(X, apar, 0, d_ready, nullptr);         // P2: net.4 -> X; net.6 is the workers' dot product
+                layer<H>(X, apar, 0u, 0, d_ready, nullptr);            // P2: net.4 -> X; net.6 is the workers' dot product
                 apar ^= 1;
             }
         }
     }
 
     // ---- workers (warps 0-7): thread (row, half) runs the epilogue of columns [16 half, 16 half + 16) of every piece
-    __device__ __forceinline__ void a_store8(int row, int kchunk, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3) {
-        *reinterpret_cast<uint4 *>(sA + (size_t)kchunk * kChunkBytes + row * 16) = make_uint4(p0, p1, p2, p3);
+    __device__ __forceinline__ void a_store8(uint32_t abuf, int row, int kchunk, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3) {
+        *reinterpret_cast<uint4 *>(sA + (size_t)abuf * G::ABytes + (size_t)kchunk * kChunkBytes + row * 16) = make_uint4(p0, p1, p2, p3);
     }
-    // A[:, c] = act(D[:, dcol + c]) for this thread's 16 columns [32j + 16 half, +16) of every piece j in [JB, JE); the
+    __device__ __forceinline__ void store_piece(uint32_t abuf, int row, int half, int j, const float (&x)[16]) {
+#pragma unroll
+        for (int qd = 0; qd < 2; ++qd)
+            a_store8(abuf, row, j * 4 + 2 * half + qd, pack_h2(x[qd * 8 + 0], x[qd * 8 + 1]), pack_h2(x[qd * 8 + 2], x[qd * 8 + 3]),
+                     pack_h2(x[qd * 8 + 4], x[qd * 8 + 5]), pack_h2(x[qd * 8 + 6], x[qd * 8 + 7]));
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(&a_rdy[abuf * kMaxChunks + j]);
+    }
+    // A[abuf][:, c] = act(D[:, dcol + c]) for this thread's 16 columns [32j + 16 half, +16) of every piece j in [JB, JE); the
     // bias is already in D.  Both halves arrive on the piece's barrier, so pieces complete one after the other and the
     // MMAs of the next layer follow one piece behind.
-    // WAIT_FREE: the previous reader of the A piece may still be in flight (no d_ready wait in between): wait a_free
-    // (a_free[j] completes twice per pass: integrator_net.2 and other_net.2 each release piece j once they have read it).
-    template <bool WAIT_FREE, int JB = 0, int JE = G::NP>
-    __device__ __forceinline__ void epilogue(int row, int half, int dcol, uint32_t free_parity) {
+    template <int JB = 0, int JE = G::NP>
+    __device__ __forceinline__ void epilogue(int row, int half, int dcol, uint32_t abuf) {
         const uint32_t taddr = tmem_base + ((uint32_t)((row / 32) * 32) << 16) + (uint32_t)(dcol + 16 * half);
         float v[2][16];
         if (JB < JE) tmem_ld16_issue(taddr + JB * 32, v[0]);
@@ -589,14 +619,25 @@ template <int KIND, int H> struct Engine {
             float(&x)[16] = v[(j - JB) & 1];
 #pragma unroll
             for (int e = 0; e < 16; ++e) x[e] = act_fn<G::kRelu>(x[e]);
-            if (WAIT_FREE) mbar_wait(&a_free[j], free_parity);
+            store_piece(abuf, row, half, j, x);
+        }
+    }
+    // modular: tanh(integrator_net.0) straight from the fp32 integrated error (one input: w * I + b on the FMA pipe);
+    // needs neither TMEM nor the tensor pipe, so it runs while the previous pass's net.0 is still accumulating.
+    template <int JB, int JE>
+    __device__ __forceinline__ void epilogue_l1i(int row, int half, int g, uint32_t abuf) {
+        const float I = sI[g * kRows + row];
 #pragma unroll
-            for (int qd = 0; qd < 2; ++qd)
-                a_store8(row, j * 4 + 2 * half + qd, pack_h2(x[qd * 8 + 0], x[qd * 8 + 1]), pack_h2(x[qd * 8 + 2], x[qd * 8 + 3]),
-                         pack_h2(x[qd * 8 + 4], x[qd * 8 + 5]), pack_h2(x[qd * 8 + 6], x[qd * 8 + 7]));
-            tc_fence_before();
-            fence_proxy_async();
-            mbar_arrive(&a_rdy[j]);
+        for (int j = JB; j < JE; ++j) {
+            const float4 *wb = reinterpret_cast<const float4 *>(sL1i + 2 * (32 * j + 16 * half));
+            float x[16];
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) {
+                const float4 t = wb[e / 2];   // (w_e, b_e, w_{e+1}, b_{e+1})
+                x[e] = tanh_fast(fmaf(t.x, I, t.y));
+                x[e + 1] = tanh_fast(fmaf(t.z, I, t.w));
+            }
+            store_piece(abuf, row, half, j, x);
         }
     }
 
@@ -635,28 +676,41 @@ template <int KIND, int H> struct Engine {
             dph ^= 1;
             tc_fence_after();
         };
-        for (int q = 0; q < passes; ++q) {
-            if constexpr (G::kModular) {
-                mbar_wait(p0_rdy, (uint32_t)q & 1u);                  // P0: Da = integrator_net.0 (net_residual.py:154)
+        if constexpr (G::kModular) {
+            // Software pipeline over passes: the first epilogue of pass q (CUDA cores only) is wrapped around the last
+            // epilogue of pass q-1, so that net.0 of pass q-1 (the one tensor-bound stretch) finishes in its shadow.
+            uint32_t ep = 0;   // running count of A-writing epilogues (A tile = ep & 1), same sequence as the MMA warp
+            for (int q = 0; q < passes; ++q) {
+                const int g = q & 1;
+                mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);              // the owners have written this pass's observation
+                epilogue_l1i<0, G::NP / 2>(row, half, g, ep & 1u);          // tanh(integrator_net.0) (net_residual.py:154), first half
+                if (q > 0) {
+                    wait_d();                                               // P3 of the previous pass: Db = net.0
+                    epilogue_dot(row, half, H, (q - 1) & 1);                // net.2 (:158) of the previous pass
+                }
+                epilogue_l1i<G::NP / 2, G::NP>(row, half, g, ep & 1u);      // second half; feeds integrator_net.2 (:155)
+                ++ep;
+                mbar_wait(l1b_rdy, (uint32_t)q & 1u);                       // Db = other_net.0 (:151)
                 tc_fence_after();
-                epilogue<false>(row, half, 0, 0);                     // tanh(Da) -> A, feeds integrator_net.2 (:155)
-                mbar_wait(l1b_rdy, (uint32_t)q & 1u);                 //     Db = other_net.0 (:151)
+                epilogue<>(row, half, H, ep & 1u);                          // tanh(Db) -> A, feeds other_net.2 (:152)
+                ++ep;
+                mbar_wait(h_rdy, (uint32_t)q & 1u);                         // P1: Da[0:H/2] = integrator_net.2 (complete long ago)
                 tc_fence_after();
-                epilogue<true>(row, half, H, 0u);                     // tanh(Db) -> A, feeds other_net.2 (:152)
-                mbar_wait(h_rdy, (uint32_t)q & 1u);                   // P1: Da[0:H/2] = integrator_net.2 (complete long ago)
-                tc_fence_after();
-                epilogue<true, 0, G::NP / 2>(row, half, 0, 1u);       // first half of cat' (:170) while other_net.2 finishes
-                wait_d();                                             // P2: Da[H/2:H] = other_net.2
-                epilogue<true, G::NP / 2, G::NP>(row, half, 0, 1u);   // second half of cat, feeds net.0 (:157)
-                wait_d();                                             // P3: Db = net.0
-                epilogue_dot(row, half, H, q & 1);                    // net.2 (:158)
-            } else {
+                epilogue<0, G::NP / 2>(row, half, 0, ep & 1u);              // first half of cat' (:170) while other_net.2 finishes
+                wait_d();                                                   // P2: Da[H/2:H] = other_net.2
+                epilogue<G::NP / 2, G::NP>(row, half, 0, ep & 1u);          // second half of cat', feeds net.0 (:157)
+                ++ep;
+            }
+            wait_d();
+            epilogue_dot(row, half, H, (passes - 1) & 1);
+        } else {
+            for (int q = 0; q < passes; ++q) {
                 const int X = (q & 1) ? H : 0, Y = (q & 1) ? 0 : H;
                 mbar_wait(p0_rdy, (uint32_t)q & 1u);
                 tc_fence_after();
-                epilogue<false>(row, half, X, 0);
+                epilogue<>(row, half, X, 0u);
                 wait_d();
-                epilogue<false>(row, half, Y, 0);
+                epilogue<>(row, half, Y, 0u);
                 wait_d();
                 epilogue_dot(row, half, X, q & 1);
             }
@@ -669,15 +723,15 @@ template <int KIND, int H> struct Engine {
         uint8_t *dst = sA + G::ObsOff + g * G::ObsGroupBytes + row * 16;
         if constexpr (G::kModular) {
             const int So = mp.S - 1;
-            __half h[4], l[4];
+            __half h[3], l[3];
             split_h(obs[0], h[0], l[0]);
             split_h(So > 1 ? obs[1] : 0.0f, h[1], l[1]);
             split_h(So > 2 ? obs[2] : 0.0f, h[2], l[2]);
-            split_h(obs[So], h[3], l[3]);
             const __half one = __float2half_rn(1.0f), zero = __float2half_rn(0.0f);
-            *reinterpret_cast<uint4 *>(dst) = make_uint4(pack_hh(h[0], h[1]), pack_hh(h[2], h[3]), pack_hh(l[0], l[1]), pack_hh(l[2], l[3]));
+            *reinterpret_cast<uint4 *>(dst) = make_uint4(pack_hh(h[0], h[1]), pack_hh(h[2], zero), pack_hh(l[0], l[1]), pack_hh(l[2], zero));
             *reinterpret_cast<uint4 *>(dst + kChunkBytes) =
-                make_uint4(pack_hh(h[0], h[1]), pack_hh(h[2], h[3]), pack_hh(one, one), pack_hh(zero, zero));
+                make_uint4(pack_hh(h[0], h[1]), pack_hh(h[2], zero), pack_hh(one, one), pack_hh(zero, zero));
+            sI[g * kRows + row] = obs[So];   // the integrated error stays fp32 (integrator_net.0 runs on the CUDA cores)
         } else {
             __align__(16) __half hl[kMaxKP];
             const int S = mp.S, KP = mp.KP, nt = mp.nterms;
