@@ -341,6 +341,14 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return y;
 }
 template <bool RELU> __device__ __forceinline__ float act_fn(float x) { return RELU ? fmaxf(x, 0.0f) : tanh_fast(x); }
+// same, but pinned in program order (asm volatile): the epilogues issue the MUFU work of the NEXT piece before the
+// stores / fence / barrier arrive of the current one, so that the MUFU queue of a warp never drains at a piece boundary
+template <bool RELU> __device__ __forceinline__ float act_pinned(float x) {
+    if (RELU) return fmaxf(x, 0.0f);
+    float y;
+    asm volatile("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
@@ -609,35 +617,50 @@ template <int KIND, int H> struct Engine {
     // MMAs of the next layer follow one piece behind.
     template <int JB = 0, int JE = G::NP>
     __device__ __forceinline__ void epilogue(int row, int half, int dcol, uint32_t abuf) {
-        const uint32_t taddr = tmem_base + ((uint32_t)((row / 32) * 32) << 16) + (uint32_t)(dcol + 16 * half);
-        float v[2][16];
-        if (JB < JE) tmem_ld16_issue(taddr + JB * 32, v[0]);
-#pragma unroll
-        for (int j = JB; j < JE; ++j) {
+        if constexpr (JB < JE) {
+            const uint32_t taddr = tmem_base + ((uint32_t)((row / 32) * 32) << 16) + (uint32_t)(dcol + 16 * half);
+            float v[2][16], x[2][16];
+            tmem_ld16_issue(taddr + JB * 32, v[0]);
             tmem_wait_ld();
-            if (j + 1 < JE) tmem_ld16_issue(taddr + (j + 1) * 32, v[(j - JB + 1) & 1]);
-            float(&x)[16] = v[(j - JB) & 1];
+            if (JB + 1 < JE) tmem_ld16_issue(taddr + (JB + 1) * 32, v[1]);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) x[e] = act_fn<G::kRelu>(x[e]);
-            store_piece(abuf, row, half, j, x);
+            for (int e = 0; e < 16; ++e) x[0][e] = act_pinned<G::kRelu>(v[0][e]);
+#pragma unroll
+            for (int j = JB; j < JE; ++j) {
+                const int cur = (j - JB) & 1;
+                if (j + 1 < JE) {   // activation of the next piece first: its MUFU work overlaps the stores below
+                    tmem_wait_ld();
+                    if (j + 2 < JE) tmem_ld16_issue(taddr + (j + 2) * 32, v[cur]);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) x[cur ^ 1][e] = act_pinned<G::kRelu>(v[cur ^ 1][e]);
+                }
+                store_piece(abuf, row, half, j, x[cur]);
+            }
         }
     }
     // modular: tanh(integrator_net.0) straight from the fp32 integrated error (one input: w * I + b on the FMA pipe);
     // needs neither TMEM nor the tensor pipe, so it runs while the previous pass's net.0 is still accumulating.
     template <int JB, int JE>
     __device__ __forceinline__ void epilogue_l1i(int row, int half, int g, uint32_t abuf) {
-        const float I = sI[g * kRows + row];
+        if constexpr (JB < JE) {
+            const float I = sI[g * kRows + row];
+            float x[2][16];
+            auto piece = [&](int j, float (&y)[16]) {
+                const float4 *wb = reinterpret_cast<const float4 *>(sL1i + 2 * (32 * j + 16 * half));
 #pragma unroll
-        for (int j = JB; j < JE; ++j) {
-            const float4 *wb = reinterpret_cast<const float4 *>(sL1i + 2 * (32 * j + 16 * half));
-            float x[16];
+                for (int e = 0; e < 16; e += 2) {
+                    const float4 t = wb[e / 2];   // (w_e, b_e, w_{e+1}, b_{e+1})
+                    y[e] = act_pinned<false>(fmaf(t.x, I, t.y));
+                    y[e + 1] = act_pinned<false>(fmaf(t.z, I, t.w));
+                }
+            };
+            piece(JB, x[0]);
 #pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-                const float4 t = wb[e / 2];   // (w_e, b_e, w_{e+1}, b_{e+1})
-                x[e] = tanh_fast(fmaf(t.x, I, t.y));
-                x[e + 1] = tanh_fast(fmaf(t.z, I, t.w));
+            for (int j = JB; j < JE; ++j) {
+                const int cur = (j - JB) & 1;
+                if (j + 1 < JE) piece(j + 1, x[cur ^ 1]);
+                store_piece(abuf, row, half, j, x[cur]);
             }
-            store_piece(abuf, row, half, j, x);
         }
     }
 
