@@ -36,13 +36,16 @@ WORKLOADS = {
                env="NonLinearWaterTankChangingParamUniformGoalIntegrator-SquareDistance-v2", K=[0.0, 0.4, -0.4, 0.0], sqrt=40),
     "ph": dict(name="pH ensemble sweep, 8M envs sharded by ensemble member (configs[3])", S=3, T=50, H=128, envs=1 << 23,
                env="PH1DChangingParamUniformGoalIntegrator-SqaureDistance-v35", K=[-0.02, 0.02, 0.035], sqrt=0),
+    "wts10": dict(name="water-tank Stacking10 + ResidualPPO-256 (the network of run_watertank_changing.sh, configs[0]) at 2^19 envs", S=30, T=200,
+                  H=256, envs=1 << 19, env="NonLinearWaterTankChangingParamUniformGoalStacking10-SquareDistance-v2",
+                  K=[0.0] * 27 + [0.0, 0.4, -0.4], sqrt=40, kind="plain"),
     "train": dict(name="full PIME residual actor-critic training, GPU-resident replay, grad allreduce (configs[4])", S=4, T=200, H=256,
                   envs=1 << 16, env="NonLinearWaterTankChangingParamUniformGoalIntegrator-SquareDistance-v2",
                   K=[0.0, 0.4, -0.4, 0.0], sqrt=40),
 }
 
-FLOPS_PER_STEP = {("modular", 256, 4): 264704, ("modular", 128, 3): 66560}  # 2 x weights, SURVEY 8a d4
-TANH_PER_STEP = {("modular", 256, 4): 1025, ("modular", 128, 3): 513}
+FLOPS_PER_STEP = {("modular", 256, 4): 264704, ("modular", 128, 3): 66560, ("plain", 256, 30): 278016}  # 2 x weights, SURVEY 8a d4/d5
+TANH_PER_STEP = {("modular", 256, 4): 1025, ("modular", 128, 3): 513, ("plain", 256, 30): 769}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (ncu --set full), keyed by (workload, envs, T); see profiles/
 NCU_DRAM_BYTES_PER_LAUNCH = {("wt", 1 << 20, 200): 6.7797e9}   # profiles/r01_ncu_summary.md (algorithmic: 6.71e9 replay rows)
 NCU_DRAM_BYTES_STEP = {"wt": 2.1359e9}   # wt_step_kernel<float>, 2^25 envs (algorithmic 1.913e9 + 8 B/env ep_return)
@@ -78,7 +81,7 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, sm_max=1965.0, src="fallback (B200_PROFILING.md)")
 
 
-def actor_state_dict(H, S, seed=0):
+def actor_state_dict(H, S, seed=0, kind="modular"):
     """Modular actor at torch's default init scale; the last layer is N(0, 0.1^2) so that the MLP is not a numerical
     no-op (the reference zero-initialises it, which would make every product zero)."""
     rng = np.random.default_rng(seed)
@@ -87,10 +90,15 @@ def actor_state_dict(H, S, seed=0):
         b = 1.0 / np.sqrt(i)
         return rng.uniform(-b, b, (o, i)).astype(np.float32), rng.uniform(-b, b, o).astype(np.float32)
     sd = {}
-    for name, o, i in [("other_net.0", H, S - 1), ("other_net.2", H // 2, H), ("integrator_net.0", H, 1),
-                       ("integrator_net.2", H // 2, H), ("net.0", H, H), ("net.2", 1, H)]:
-        sd[name + ".weight"], sd[name + ".bias"] = lin(o, i)
-    sd["net.2.weight"] = rng.normal(0, 0.1, (1, H)).astype(np.float32)
+    if kind == "plain":
+        for name, o, i in [("net.0", H, S), ("net.2", H, H), ("net.4", H, H), ("net.6", 1, H)]:
+            sd[name + ".weight"], sd[name + ".bias"] = lin(o, i)
+        sd["net.6.weight"] = rng.normal(0, 0.1, (1, H)).astype(np.float32)
+    else:
+        for name, o, i in [("other_net.0", H, S - 1), ("other_net.2", H // 2, H), ("integrator_net.0", H, 1),
+                           ("integrator_net.2", H // 2, H), ("net.0", H, H), ("net.2", 1, H)]:
+            sd[name + ".weight"], sd[name + ".bias"] = lin(o, i)
+        sd["net.2.weight"] = rng.normal(0, 0.1, (1, H)).astype(np.float32)
     sd["a_std_log"] = np.array([[-0.5]], np.float32)
     return sd
 
@@ -148,7 +156,8 @@ def resolve(args, world=1):
     w["H"] = args.net_dim or w["H"]
     w["T"] = args.T or w["T"]
     w["n"] = args.envs or (max(1, w["envs"] // world) if args.workload == "ph" else w["envs"])
-    w["actor"] = f"ResidualIntegratorModularPPO-{w['H']}"
+    w.setdefault("kind", "modular")
+    w["actor"] = ("ResidualIntegratorModularPPO-" if w["kind"] == "modular" else "ResidualPPO-") + str(w["H"])
     return w
 
 
@@ -254,9 +263,13 @@ def run_b200(args):
     n, T, H, S = w["n"], w["T"], w["H"], w["S"]
     is_wt = args.workload == "wt"
     K = np.array(w["K"])
-    sd = actor_state_dict(H, S)
-    actor = V.ActorPack("modular", S, H, 1).update(sd)
-    if is_wt:
+    kind = w["kind"]
+    sd = actor_state_dict(H, S, kind=w["kind"])
+    actor = V.ActorPack(w["kind"], S, H, 1).update(sd)
+    if args.workload == "wts10":
+        env = V.WaterTankVec(n, dtype=torch.float32, obs_mode="stacking", num_stack=10, reward_type="square_distance",
+                             noise_scale=0.01, seed=0, env_offset=rank * n)
+    elif is_wt:
         env = V.WaterTankVec(n, dtype=torch.float32, obs_mode="integrator", reward_type="square_distance", noise_scale=0.01,
                              seed=0, env_offset=rank * n)
     else:
@@ -331,14 +344,14 @@ def run_b200(args):
                "d2h_bytes_per_step": int(d2h),
                "api": "WaterTankVec.rollout_host -> pime_wt_rollout_host_f32 (pinned host state in, ep_return + final state out)"}
 
-    kname = f"rollout_kernel<{'WtGlue' if is_wt else 'PhGlue'}<float>, modular, {H}>"
+    kname = f"rollout_kernel<{'PhGlue' if args.workload == 'ph' else 'WtGlue'}<float>, {kind}, {H}>"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak" if is_wt or args.envs else "strong", "vs_baseline": None,
+            "scaling": "strong" if (args.workload == "ph" and not args.envs) else "weak", "vs_baseline": None,
             "dtype": "f32 (plant, prior, obs, first and last actor layer; hidden layers: f16 tensor-core operands, f32 accumulate)",
             "data": "synthetic",
             "config": {"workload": w["name"], "envs_per_gpu": n, "T": T, "actor": w["actor"], "env": w["env"],
-                       "noise_scale": 0.01 if is_wt else 0.0,
+                       "noise_scale": 0.0 if args.workload == "ph" else 0.01,
                        "policy": "stochastic (explore_env)", "replay": "GPU-resident, time-major [T,n,S]+[T,n,4] fp32",
                        "l2": f"each step streams {(bs.numel() + bo.numel()) * 4 / 1e9:.2f} GB of replay rows through L2 (>> 126 MB), "
                              "which flushes it between timed steps",
@@ -349,7 +362,7 @@ def run_b200(args):
         line["e2e"] = e2e
 
     if rank == 0:
-        flops = FLOPS_PER_STEP.get(("modular", H, S))
+        flops = FLOPS_PER_STEP.get((kind, H, S))
         step_ms = float(np.mean(kernel_ms))
         if flops:
             ach = n * T * flops / (step_ms * 1e-3) / 1e12
@@ -359,14 +372,14 @@ def run_b200(args):
                                 "note": "the binding unit is the MUFU pipe (one tanh per hidden activation), see sfu; HBM traffic is "
                                         "the replay rows only (traffic = dram bytes of one launch, ncu --set full, profiles/)"}
             sm_mhz = clocks.get("sm_mhz") or pk["sm_max"]
-            mufu = n * T * (TANH_PER_STEP[("modular", H, S)] - 1 + w["sqrt"] + 6) / (step_ms * 1e-3)
+            mufu = n * T * (TANH_PER_STEP[(kind, H, S)] - 1 + w["sqrt"] + 6) / (step_ms * 1e-3)
             mufu_peak = 148 * 16 * sm_mhz * 1e6
             line["sfu"] = {"achieved_gops": mufu / 1e9, "peak_gops": mufu_peak / 1e9, "frac": mufu / mufu_peak,
                            "note": "MUFU ops/s (hidden tanh + plant sqrt + Box-Muller) vs 148 SM x 16/clk at the median SM clock "
                                    "under load (tanh.approx microbenchmark on this pool: 16.3 per clk per SM)"}
         if not args.no_aux and is_wt:
             line["roofline_step"] = aux_step_rooflines(V, pk)
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.workload in ("wt", "ph"):
             line["cpu_baseline"] = cpu_baseline(w, args.cpu_seconds, sd)
         print(json.dumps(line), flush=True)
     if world > 1:
