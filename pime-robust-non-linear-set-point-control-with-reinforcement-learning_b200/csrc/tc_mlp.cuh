@@ -52,7 +52,7 @@ constexpr int kHeaderBytes = 4096;         // head of the pack: block list (kMax
 constexpr int kOutWOff = 512;              // fp32 [H] weight vector + bias of the last Linear(H -> 1), inside the header
 constexpr int kL1iOff = 1600;              // modular: fp32 (w, b)[H] of integrator_net.0 (one input: runs on the CUDA cores)
 constexpr int kMaxKP = 64;                 // widest first-layer operand (2 x 31 inputs + 2)
-constexpr int kMaxChunks = 8;              // 32-column pieces of a layer (H <= 256): the granularity of the MMA pipelining
+constexpr int kMaxChunks = 4;              // 64-column chunks (two pieces) of a layer (H <= 256): the granularity of the MMA pipelining
 
 // ------------------------------------------------------------------------------------------------ block program
 enum : uint32_t {
@@ -532,8 +532,8 @@ template <int KIND, int H> struct Engine {
     __device__ __forceinline__ void layer(uint32_t d_col, uint32_t apar, uint32_t abuf, int lag, uint64_t *e1, uint64_t *e2) {
         constexpr int K16 = H / 16, kpb = blk_k16(N, K16);
         const uint32_t a_tile = abuf * (uint32_t)G::ABytes;
-        int waited = (K_LO * 16) / 32;   // pieces below K_LO were waited on by the call that issued them
-        auto need = [&](int upto) {      // pieces [0, upto) of the feeding epilogue are in shared memory
+        int waited = (K_LO * 16) / 64;   // chunks below K_LO were waited on by the call that issued them
+        auto need = [&](int upto) {      // chunks [0, upto) of the feeding epilogue are in shared memory
             if (waited < upto) {
                 for (; waited < upto; ++waited) mbar_wait(&a_rdy[abuf * kMaxChunks + waited], apar);
                 tc_fence_after();
@@ -545,7 +545,7 @@ template <int KIND, int H> struct Engine {
         }
 #pragma unroll
         for (int k = K_LO; k < K_HI; k += kpb) {
-            need(((k + kpb) * 16 + 31) / 32);   // pieces touched by K columns [16k, 16(k+kpb))
+            need(((k + kpb) * 16 + 63) / 64);   // chunks touched by K columns [16k, 16(k+kpb))
             const bool last = k + kpb >= K_HI;
             blk<N, false>(a_tile + (uint32_t)k * kK16Bytes, kpb, d_col, last ? e1 : nullptr, last ? e2 : nullptr);
         }
@@ -608,13 +608,15 @@ template <int KIND, int H> struct Engine {
         for (int qd = 0; qd < 2; ++qd)
             a_store8(abuf, row, j * 4 + 2 * half + qd, pack_h2(x[qd * 8 + 0], x[qd * 8 + 1]), pack_h2(x[qd * 8 + 2], x[qd * 8 + 3]),
                      pack_h2(x[qd * 8 + 4], x[qd * 8 + 5]), pack_h2(x[qd * 8 + 6], x[qd * 8 + 7]));
-        tc_fence_before();
-        fence_proxy_async();
-        mbar_arrive(&a_rdy[abuf * kMaxChunks + j]);
+        if ((j & 1) || j == G::NP - 1) {   // one fence + arrive per 64-column chunk (its last piece)
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(&a_rdy[abuf * kMaxChunks + (j >> 1)]);
+        }
     }
     // A[abuf][:, c] = act(D[:, dcol + c]) for this thread's 16 columns [32j + 16 half, +16) of every piece j in [JB, JE); the
-    // bias is already in D.  Both halves arrive on the piece's barrier, so pieces complete one after the other and the
-    // MMAs of the next layer follow one piece behind.
+    // bias is already in D.  Both halves arrive on the barrier of the 64-column chunk, and the MMAs of the next layer
+    // follow one chunk behind.
     template <int JB = 0, int JE = G::NP>
     __device__ __forceinline__ void epilogue(int row, int half, int dcol, uint32_t abuf) {
         if constexpr (JB < JE) {
