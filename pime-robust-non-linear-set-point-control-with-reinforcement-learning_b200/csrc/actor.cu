@@ -63,11 +63,15 @@ __global__ void __launch_bounds__(tc::kThreads, 1) actor_forward_kernel(tc::MlpP
     } else if (warp < 12) {
         const int row = tid - tc::kWorkerThreads;
         float o[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) o[k] = 0.0f;
 #pragma unroll 1
         for (int g = 0; g < 2; ++g) {
             const int64_t i = (int64_t)blockIdx.x * tc::kTileEnvs + g * tc::kRows + row;
             const int64_t ii = i < n ? i : n - 1;
-            for (int k = 0; k < mp.S; ++k) o[k] = obs[ii * mp.S + k];
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+                if (k < mp.S) o[k] = obs[ii * mp.S + k];
             eng.write_obs(row, g, o);
         }
 #pragma unroll 1

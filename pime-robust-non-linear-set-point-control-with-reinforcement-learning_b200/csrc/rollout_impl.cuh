@@ -28,7 +28,12 @@ struct RolloutParams {
 };
 
 // ------------------------------------------------------------------------------------------------ plant glue
-template <typename T> struct WtGlue {
+// STACK selects the observation-history variant (NonLinearWaterTank...Stacking): the last num_stack frames of
+// (h1, h2, r) live in registers (every loop below is unrolled to the maximum, 10 frames, and predicated), which keeps
+// them out of local memory; the goal / integrator variant carries no history at all.
+constexpr int kMaxFrames = 30;
+
+template <typename T, bool STACK> struct WtGlue {
     using Real = T;
     WtConst<T> c;
     T *h1, *h2, *r, *I, *a1, *a2, *Kp, *ep_return, *frames;
@@ -39,12 +44,9 @@ template <typename T> struct WtGlue {
         WtEnv<T> e;
         T ret;
         uint32_t episode;
-        T fr[30];  // stacking only (local memory); obs history, oldest first
+        T fr[STACK ? kMaxFrames : 1];  // obs history, oldest first
     };
 
-    __device__ __forceinline__ int obs_dim() const {
-        return c.obs_mode == PIME_WT_OBS_GOAL ? 3 : (c.obs_mode == PIME_WT_OBS_INTEGRATOR ? 4 : 3 * c.num_stack);
-    }
     __device__ __forceinline__ void load(Env &v, int64_t i, int64_t n) const {
         v.e.h1 = h1[i]; v.e.h2 = h2[i]; v.e.r = r[i];
         v.e.I = c.obs_mode == PIME_WT_OBS_INTEGRATOR ? I[i] : (T)0;
@@ -52,8 +54,11 @@ template <typename T> struct WtGlue {
         v.e.t = t[i];
         v.ret = ep_return ? ep_return[i] : (T)0;
         v.episode = episode[i];
-        if (c.obs_mode == PIME_WT_OBS_STACKING)
-            for (int j = 0; j < 3 * c.num_stack; ++j) v.fr[j] = frames[(int64_t)j * n + i];
+        if constexpr (STACK) {
+            const int m = 3 * c.num_stack;
+#pragma unroll
+            for (int j = 0; j < kMaxFrames; ++j) v.fr[j] = j < m ? frames[(int64_t)j * n + i] : (T)0;
+        }
     }
     __device__ __forceinline__ void store(const Env &v, int64_t i, int64_t n) const {
         h1[i] = v.e.h1; h2[i] = v.e.h2; r[i] = v.e.r;
@@ -62,26 +67,34 @@ template <typename T> struct WtGlue {
         t[i] = v.e.t;
         if (ep_return) ep_return[i] = v.ret;
         episode[i] = v.episode;
-        if (c.obs_mode == PIME_WT_OBS_STACKING)
-            for (int j = 0; j < 3 * c.num_stack; ++j) frames[(int64_t)j * n + i] = v.fr[j];
+        if constexpr (STACK) {
+            const int m = 3 * c.num_stack;
+#pragma unroll
+            for (int j = 0; j < kMaxFrames; ++j)
+                if (j < m) frames[(int64_t)j * n + i] = v.fr[j];
+        }
     }
-    // float32(obs): elegantrl/env.py:46,72
-    __device__ __forceinline__ void observe(const Env &v, float *obs) const {
-        if (c.obs_mode == PIME_WT_OBS_STACKING) {
-            for (int j = 0; j < 3 * c.num_stack; ++j) obs[j] = (float)v.fr[j];
+    // float32(obs): elegantrl/env.py:46,72.  obs[] is indexed with compile-time indices only (registers).
+    __device__ __forceinline__ void observe(const Env &v, float (&obs)[kMaxS]) const {
+        if constexpr (STACK) {
+#pragma unroll
+            for (int j = 0; j < kMaxFrames; ++j) obs[j] = (float)v.fr[j];
         } else {
             obs[0] = (float)v.e.h1; obs[1] = (float)v.e.h2; obs[2] = (float)v.e.r;
-            if (c.obs_mode == PIME_WT_OBS_INTEGRATOR) obs[3] = (float)v.e.I;
+            obs[3] = c.obs_mode == PIME_WT_OBS_INTEGRATOR ? (float)v.e.I : 0.0f;
         }
     }
     __device__ __forceinline__ bool uses_process_noise() const { return c.noise_scale > (T)0; }
     __device__ __forceinline__ T noise_sigma() const { return c.noise_scale; }
     __device__ __forceinline__ bool advance(Env &v, T action, T nz1, T nz2, T &rew, bool &done) const {
         wt_advance(c, v.e, action, nz1, nz2, rew, done);
-        if (c.obs_mode == PIME_WT_OBS_STACKING) {  // frames.append(state) (nonlinear_watertank.py:1145-1146)
+        if constexpr (STACK) {  // frames.append(state) (nonlinear_watertank.py:1145-1146)
             const int m = 3 * c.num_stack;
-            for (int j = 0; j < m - 3; ++j) v.fr[j] = v.fr[j + 3];
-            v.fr[m - 3] = v.e.h1; v.fr[m - 2] = v.e.h2; v.fr[m - 1] = v.e.r;
+#pragma unroll
+            for (int j = 0; j < kMaxFrames - 3; ++j) v.fr[j] = j < m - 3 ? v.fr[j + 3] : v.fr[j];
+#pragma unroll
+            for (int j = 0; j < kMaxFrames; j += 3)
+                if (j == m - 3) { v.fr[j] = v.e.h1; v.fr[j + 1] = v.e.h2; v.fr[j + 2] = v.e.r; }
         }
         return true;
     }
@@ -91,8 +104,12 @@ template <typename T> struct WtGlue {
         reset_uniforms(seed, index, v.episode, u);
         wt_reset(c, v.e, u, true);
         v.episode += 1;
-        if (c.obs_mode == PIME_WT_OBS_STACKING)
-            for (int j = 0; j < c.num_stack; ++j) { v.fr[3 * j] = v.e.h1; v.fr[3 * j + 1] = v.e.h2; v.fr[3 * j + 2] = v.e.r; }
+        if constexpr (STACK) {
+            const int m = 3 * c.num_stack;
+#pragma unroll
+            for (int j = 0; j < kMaxFrames; j += 3)
+                if (j < m) { v.fr[j] = v.e.h1; v.fr[j + 1] = v.e.h2; v.fr[j + 2] = v.e.r; }
+        }
         return true;
     }
 };
@@ -110,7 +127,6 @@ template <typename T> struct PhGlue {
         T qww, qc, ret;
         uint32_t episode;
     };
-    __device__ __forceinline__ int obs_dim() const { return c.integrator_mode == PIME_PH_NO_INTEGRATOR ? 2 : 3; }
     __device__ __forceinline__ void load(Env &v, int64_t i, int64_t) const {
         v.e.x = x[i]; v.e.y = y[i]; v.e.r = r[i];
         v.e.I = c.integrator_mode != PIME_PH_NO_INTEGRATOR ? I[i] : (T)0;
@@ -129,9 +145,9 @@ template <typename T> struct PhGlue {
         if (ep_return) ep_return[i] = v.ret;
         episode[i] = v.episode;
     }
-    __device__ __forceinline__ void observe(const Env &v, float *obs) const {
+    __device__ __forceinline__ void observe(const Env &v, float (&obs)[kMaxS]) const {
         obs[0] = (float)v.e.y; obs[1] = (float)v.e.r;
-        if (c.integrator_mode != PIME_PH_NO_INTEGRATOR) obs[2] = (float)v.e.I;
+        obs[2] = c.integrator_mode != PIME_PH_NO_INTEGRATOR ? (float)v.e.I : 0.0f;
     }
     __device__ __forceinline__ bool uses_process_noise() const { return false; }
     __device__ __forceinline__ T noise_sigma() const { return (T)0; }
@@ -157,8 +173,8 @@ template <typename Plant> struct Stepper {
     double s_ret = 0.0, s_ret2 = 0.0, s_cnt = 0.0, s_err = 0.0, s_rew = 0.0, s_steps = 0.0;
     bool fault = false;
 
-    __device__ __forceinline__ void step(const Plant &plant, const RolloutParams &rp, typename Plant::Env &env, const float *obs,
-                                         float a_avg, int s, int64_t ii, bool live) {
+    __device__ __forceinline__ void step(const Plant &plant, const RolloutParams &rp, typename Plant::Env &env,
+                                         const float (&obs)[kMaxS], float a_avg, int s, int64_t ii, bool live) {
         const int64_t n = rp.n;
         const int S = rp.S;
         // ---- noise
@@ -182,12 +198,16 @@ template <typename Plant> struct Stepper {
         T action;
         if (rp.deterministic) {
             float prior = 0.0f;
-            for (int k = 0; k < S; ++k) prior = fmaf(obs[k], (float)rp.priorK[k], prior);
+#pragma unroll
+            for (int k = 0; k < kMaxS; ++k)
+                if (k < S) prior = fmaf(obs[k], (float)rp.priorK[k], prior);
             a_raw = a_avg;
             action = (T)(tanhf(a_avg) + prior);
         } else {
             T prior = (T)0;
-            for (int k = 0; k < S; ++k) prior = N::add(prior, N::mul((T)obs[k], (T)rp.priorK[k]));
+#pragma unroll
+            for (int k = 0; k < kMaxS; ++k)
+                if (k < S) prior = N::add(prior, N::mul((T)obs[k], (T)rp.priorK[k]));
             a_raw = a_avg + eps * rp.a_std;   // net_residual.py:176-180
             action = N::add((T)tanhf(a_raw), prior);
         }
@@ -199,8 +219,17 @@ template <typename Plant> struct Stepper {
         if (live) {
             if (rp.buf_state) {  // replay row (agent_residual.py:64-65; replay.py:278-291), time-major
                 float *bs = rp.buf_state + q * S;
-                if (S == 4) *reinterpret_cast<float4 *>(bs) = make_float4(obs[0], obs[1], obs[2], obs[3]);
-                else for (int k = 0; k < S; ++k) bs[k] = obs[k];
+                if (S == 4) {
+                    *reinterpret_cast<float4 *>(bs) = make_float4(obs[0], obs[1], obs[2], obs[3]);
+                } else if ((S & 1) == 0) {   // rows of an even number of floats are 8-byte aligned
+#pragma unroll
+                    for (int k = 0; k < kMaxS; k += 2)
+                        if (k < S) *reinterpret_cast<float2 *>(bs + k) = make_float2(obs[k], obs[k + 1]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kMaxS; ++k)
+                        if (k < S) bs[k] = obs[k];
+                }
                 *reinterpret_cast<float4 *>(rp.buf_other + q * 4) =
                     make_float4((float)((double)rew * rp.reward_scale), done ? 0.0f : (float)rp.gamma, a_raw, eps);
             }

@@ -19,18 +19,28 @@ int wt_rollout_impl(const pime_wt_config *cfg, int64_t n, const pime_wt_state *s
     if (int rc = fill_rollout_params(args, n, S, rp, L)) return rc;
     if (int rc = require_device()) return rc;
     if (n == 0) return PIME_OK;
-    WtGlue<T> g;
-    g.c = make_wt_const<T>(*cfg);
-    g.h1 = (T *)st->h1; g.h2 = (T *)st->h2; g.r = (T *)st->r; g.I = (T *)st->I;
-    g.a1 = (T *)st->a1; g.a2 = (T *)st->a2; g.Kp = (T *)st->Kp;
-    g.ep_return = (T *)st->ep_return; g.frames = (T *)st->frames; g.t = st->t; g.episode = st->episode;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!rp.has_actor) return launch_rollout_prior<WtGlue<T>>(g, rp, s);
+    auto fill = [&](auto &g) {
+        g.c = make_wt_const<T>(*cfg);
+        g.h1 = (T *)st->h1; g.h2 = (T *)st->h2; g.r = (T *)st->r; g.I = (T *)st->I;
+        g.a1 = (T *)st->a1; g.a2 = (T *)st->a2; g.Kp = (T *)st->Kp;
+        g.ep_return = (T *)st->ep_return; g.frames = (T *)st->frames; g.t = st->t; g.episode = st->episode;
+    };
+    if (cfg->obs_mode == PIME_WT_OBS_STACKING) {   // observation history: plain actor only (the modular one needs the integrator)
+        WtGlue<T, true> g;
+        fill(g);
+        if (!rp.has_actor) return launch_rollout_prior<WtGlue<T, true>>(g, rp, s);
+        PIME_REQUIRE(args->actor->kind == PIME_ACTOR_PLAIN, "the stacking observation goes with the plain actor");
+        return launch_rollout_k<WtGlue<T, true>, PIME_ACTOR_PLAIN>(g, &L, args->actor_pack, rp, L.H, s);
+    }
+    WtGlue<T, false> g;
+    fill(g);
+    if (!rp.has_actor) return launch_rollout_prior<WtGlue<T, false>>(g, rp, s);
     if (args->actor->kind == PIME_ACTOR_MODULAR) {
         PIME_REQUIRE(cfg->obs_mode == PIME_WT_OBS_INTEGRATOR, "the modular actor needs the integrator observation");
-        return launch_rollout_k<WtGlue<T>, PIME_ACTOR_MODULAR>(g, &L, args->actor_pack, rp, L.H, s);
+        return launch_rollout_k<WtGlue<T, false>, PIME_ACTOR_MODULAR>(g, &L, args->actor_pack, rp, L.H, s);
     }
-    return launch_rollout_k<WtGlue<T>, PIME_ACTOR_PLAIN>(g, &L, args->actor_pack, rp, L.H, s);
+    return launch_rollout_k<WtGlue<T, false>, PIME_ACTOR_PLAIN>(g, &L, args->actor_pack, rp, L.H, s);
 }
 
 }  // namespace pime

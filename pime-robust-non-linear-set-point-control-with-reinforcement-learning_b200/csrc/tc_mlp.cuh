@@ -51,7 +51,7 @@ constexpr int kMaxBlocks = 24;
 constexpr int kHeaderBytes = 4096;         // head of the pack: block list (kMaxBlocks x 16 B), then the fp32 layers
 constexpr int kOutWOff = 512;              // fp32 [H] weight vector + bias of the last Linear(H -> 1), inside the header
 constexpr int kL1iOff = 1600;              // modular: fp32 (w, b)[H] of integrator_net.0 (one input: runs on the CUDA cores)
-constexpr int kMaxKP = 64;                 // widest first-layer operand (2 x 31 inputs + 2)
+constexpr int kMaxKP = 80;                 // widest first-layer operand (2 terms x stride 32 + 2, padded to 16)
 constexpr int kMaxChunks = 4;              // 64-column chunks (two pieces) of a layer (H <= 256): the granularity of the MMA pipelining
 
 // ------------------------------------------------------------------------------------------------ block program
@@ -196,9 +196,11 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
         int o = 0;
         for (int j = 0; j < 8; ++j) { L.src[j] = o; o += sizes[j]; }
         L.param_count = o;
-        L.nin = S;
-        L.nterms = 3 * S + 2 <= 32 ? 3 : 2;
-        L.KP = ((L.nterms * S + 2 + 15) / 16) * 16;
+        // first-layer operand with a compile-time stride per term (the owners build it from registers):
+        //   S <= 10: [hi(16) | lo(16) | hi(16) | 1 1]  K = 64;   S <= 16: [hi(16) | lo(16) | 1 1]  K = 48;   else [hi(32) | lo(32) | 1 1]  K = 80
+        L.nin = S <= 16 ? 16 : 32;
+        L.nterms = S <= 10 ? 3 : 2;
+        L.KP = ((L.nterms * L.nin + 2 + 15) / 16) * 16;
         if (L.KP > kMaxKP) return false;
         l1(H, L.src[0], S, L.src[1], 0, S, Da);                            // P0 net.0 -> Da
         bias(H, H, L.src[3], Db); hid(H, H, L.src[2], Db);                 // P1 net.2 -> Db
@@ -583,7 +585,7 @@ template <int KIND, int H> struct Engine {
                 mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);
                 tc_fence_after();
                 const int K16 = mp.KP / 16;                            // P0: net.0 -> X (first-layer operand K = KP)
-                constexpr int kpb = blk_k16(H, 4);
+                constexpr int kpb = blk_k16(H, kMaxKP / 16);
                 for (int k = 0; k < K16; k += kpb) {
                     const int kk = K16 - k < kpb ? K16 - k : kpb;
                     uint64_t *x = k + kpb >= K16 ? p0_rdy : nullptr;
@@ -742,9 +744,32 @@ template <int KIND, int H> struct Engine {
         }
     }
 
+    // plain / critic first-layer operand [hi(STRIDE) | lo(STRIDE) | hi(STRIDE) (3 terms) | 1 1 | 0 ...]: every index is a
+    // compile-time constant, so obs[] and the operand stay in registers
+    template <int STRIDE> __device__ __forceinline__ void write_obs_plain(uint8_t *dst, const float (&obs)[32]) {
+        const int S = mp.S, nt = mp.nterms, KP = mp.KP;
+        const uint32_t one2 = 0x3C003C00u;   // (1.0, 1.0) fp16
+#pragma unroll
+        for (int kc = 0; kc < kMaxKP / 8; ++kc) {
+            if (kc * 8 < KP) {
+                uint32_t w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int p = kc * 8 + 2 * i, t = p / STRIDE, c = p % STRIDE;   // two consecutive positions, same term
+                    __half a, b, la, lb;
+                    split_h(c < S && c < 32 ? obs[c < 32 ? c : 0] : 0.0f, a, la);
+                    split_h(c + 1 < S && c + 1 < 32 ? obs[c + 1 < 32 ? c + 1 : 0] : 0.0f, b, lb);
+                    const uint32_t hi = pack_hh(a, b), lo = pack_hh(la, lb);
+                    w[i] = t >= nt ? (p == nt * STRIDE ? one2 : 0u) : (t == 1 ? lo : hi);
+                }
+                *reinterpret_cast<uint4 *>(dst + (size_t)kc * kChunkBytes) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+    }
+
     // ---- owners (warps 8-11): thread r owns row r of both groups
     // first-layer operand of this env: [in_hi | in_lo | in_hi (3 terms) | 1 1 | 0 ...]  (see the file header)
-    __device__ __forceinline__ void write_obs(int row, int g, const float *obs) {
+    __device__ __forceinline__ void write_obs(int row, int g, const float (&obs)[32]) {
         uint8_t *dst = sA + G::ObsOff + g * G::ObsGroupBytes + row * 16;
         if constexpr (G::kModular) {
             const int So = mp.S - 1;
@@ -758,22 +783,8 @@ template <int KIND, int H> struct Engine {
                 make_uint4(pack_hh(h[0], h[1]), pack_hh(h[2], zero), pack_hh(one, one), pack_hh(zero, zero));
             sI[g * kRows + row] = obs[So];   // the integrated error stays fp32 (integrator_net.0 runs on the CUDA cores)
         } else {
-            __align__(16) __half hl[kMaxKP];
-            const int S = mp.S, KP = mp.KP, nt = mp.nterms;
-#pragma unroll 1
-            for (int k = 0; k < KP; ++k) hl[k] = __float2half_rn(0.0f);
-#pragma unroll 1
-            for (int k = 0; k < S; ++k) {
-                __half hi, lo;
-                split_h(obs[k], hi, lo);
-                hl[k] = hi;
-                hl[S + k] = lo;
-                if (nt == 3) hl[2 * S + k] = hi;
-            }
-            hl[nt * S] = __float2half_rn(1.0f);
-            hl[nt * S + 1] = __float2half_rn(1.0f);
-            const uint4 *qv = reinterpret_cast<const uint4 *>(hl);
-            for (int kc = 0; kc < KP / 8; ++kc) *reinterpret_cast<uint4 *>(dst + (size_t)kc * kChunkBytes) = qv[kc];
+            if (mp.nin == 16) write_obs_plain<16>(dst, obs);
+            else write_obs_plain<32>(dst, obs);
         }
         fence_proxy_async();
         mbar_arrive(&o_rdy[g]);
