@@ -194,6 +194,12 @@ typedef struct pime_actor_config {
 int64_t pime_actor_param_count(const pime_actor_config *cfg);
 int64_t pime_actor_pack_bytes(const pime_actor_config *cfg);
 
+/* Host-only introspection of the packed image: the list of streamed weight blocks in consumption order, four int32 per
+ * block (MMA N, number of K=16 slices, first TMEM column, bytes).  Returns the number of blocks (<= max_blocks are
+ * written) or -1 for unsupported dimensions.  Used by the tests to check the kernel's static MMA program against the
+ * pack layout without a GPU. */
+int32_t pime_actor_block_list(const pime_actor_config *cfg, int32_t *out, int32_t max_blocks);
+
 /* Re-pack fp32 torch-layout parameters (device, state_dict order) into the kernel image: fp32 first-layer /
  * bias / output-layer vectors plus fp16 hidden-layer weights pre-tiled in the tcgen05 shared-memory operand
  * layout so that one cp.async.bulk (TMA) copy brings a ready-to-use B tile. */

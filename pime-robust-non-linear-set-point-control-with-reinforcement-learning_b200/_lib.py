@@ -69,7 +69,7 @@ SYMBOLS = [
     "pime_ph_default_config", "pime_ph_table_build", "pime_ph_update_system_f32", "pime_ph_update_system_f64",
     "pime_ph_reset_f32", "pime_ph_reset_f64", "pime_ph_step_f32", "pime_ph_step_f64",
     "pime_prior_action_f32", "pime_prior_action_f64",
-    "pime_actor_param_count", "pime_actor_pack_bytes", "pime_actor_pack", "pime_actor_forward",
+    "pime_actor_param_count", "pime_actor_pack_bytes", "pime_actor_block_list", "pime_actor_pack", "pime_actor_forward",
     "pime_wt_rollout_f32", "pime_wt_rollout_f64", "pime_ph_rollout_f32", "pime_ph_rollout_f64",
     "pime_gae_scan", "pime_reduce_episode_stats_f32", "pime_reduce_episode_stats_f64",
     "pime_wt_rollout_host_f32", "pime_abi_version", "pime_last_error", "pime_device_info", "pime_philox_probe",

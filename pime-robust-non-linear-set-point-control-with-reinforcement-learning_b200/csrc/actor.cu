@@ -130,6 +130,18 @@ int64_t pime_actor_pack_bytes(const pime_actor_config *cfg) {
     return L.total_bytes;
 }
 
+int32_t pime_actor_block_list(const pime_actor_config *cfg, int32_t *out, int32_t max_blocks) {
+    tc::PackLayout L;
+    if (!cfg || !tc::make_pack_layout(*cfg, L)) return -1;
+    for (int b = 0; b < L.nblk && b < max_blocks && out; ++b) {
+        out[4 * b + 0] = L.blk[b].nb8 * 8;
+        out[4 * b + 1] = L.blk[b].k16s;
+        out[4 * b + 2] = L.blk[b].d_col;
+        out[4 * b + 3] = L.blk[b].bytes16 * 16;
+    }
+    return L.nblk;
+}
+
 int pime_actor_pack(const pime_actor_config *cfg, const float *params, void *pack, void *stream) {
     PIME_REQUIRE(cfg && params && pack, "null pointer");
     tc::PackLayout L;

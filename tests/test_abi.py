@@ -125,3 +125,46 @@ def test_product_never_touches_the_oracle():
     assert not offenders, offenders
     out = subprocess.run(["ldd", os.path.join(pkg, "libpime_b200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def _device_program(kind, H, S):
+    """Python restatement of Engine::mma_loop (csrc/tc_mlp.cuh): the (N, k16s, d_col) sequence the MMA warp issues per pass."""
+    MAXB = 16384
+    Hh, K16, Da, Db = H // 2, H // 16, 0, H
+
+    def blk_k16(N, K):
+        return min(MAXB // (N * 32), K)
+
+    def layer(N, d, k_lo=0, k_hi=None, bias=True):
+        out = [(N, 1, d)] if bias else []
+        kpb = blk_k16(N, K16)
+        k_hi = K16 if k_hi is None else k_hi
+        out += [(N, kpb, d) for _ in range(k_lo, k_hi, kpb)]
+        return out
+
+    if kind == 1:   # modular
+        kpb = blk_k16(Hh, K16)
+        ks = ((K16 // 2) // kpb) * kpb
+        return (layer(Hh, Da, 0, ks, True) + [(H, 1, Db)] + layer(Hh, Da, ks, K16, False) + layer(Hh, Da + Hh) + layer(H, Db))
+    nin = 16 if S <= 16 else 32
+    KP = ((((3 if S <= 10 else 2) * nin + 2) + 15) // 16) * 16
+    kpb = blk_k16(H, 5)
+    p0 = [(H, min(kpb, KP // 16 - k), Da) for k in range(0, KP // 16, kpb)]
+    return p0 + layer(H, Db) + layer(H, Da)     # even pass: X = Da, Y = Db (the pack lists the even pass)
+
+
+@pytest.mark.parametrize("kind,S", [(1, 4), (1, 3), (1, 2), (0, 3), (0, 4), (0, 12), (0, 16), (0, 17), (0, 30), (0, 31), (2, 3), (2, 4), (2, 30)])
+@pytest.mark.parametrize("H", [32, 64, 128, 256])
+def test_pack_block_list_matches_the_kernels_static_mma_program(L, kind, S, H):
+    """The TMA producer streams the pack's block list; the MMA warp runs a static program.  They must agree block for
+    block (a mismatch deadlocks the kernel): checked here without a GPU for every supported shape."""
+    cfg = L.ActorConfig(kind=kind, state_dim=S, mid_dim=H, integrator_dim=1 if kind == 1 else 0)
+    buf = (C.c_int32 * (4 * 64))()
+    n = L.lib().pime_actor_block_list(C.byref(cfg), buf, 64)
+    assert 0 < n <= 24
+    got = [(buf[4 * b], buf[4 * b + 1], buf[4 * b + 2]) for b in range(n)]
+    assert got == _device_program(kind, H, S)
+    sizes = [buf[4 * b + 3] for b in range(n)]
+    assert all(0 < s <= 16384 and s == N * k * 32 for s, (N, k, _) in zip(sizes, got))
+    assert sum(sizes) + 4096 == L.lib().pime_actor_pack_bytes(C.byref(cfg))
+    assert all(d + N <= 2 * H for N, _, d in got)              # accumulators stay inside the two TMEM buffers
