@@ -200,9 +200,12 @@ int64_t pime_actor_pack_bytes(const pime_actor_config *cfg);
  * pack layout without a GPU. */
 int32_t pime_actor_block_list(const pime_actor_config *cfg, int32_t *out, int32_t max_blocks);
 
-/* Re-pack fp32 torch-layout parameters (device, state_dict order) into the kernel image: fp32 first-layer /
- * bias / output-layer vectors plus fp16 hidden-layer weights pre-tiled in the tcgen05 shared-memory operand
- * layout so that one cp.async.bulk (TMA) copy brings a ready-to-use B tile. */
+/* Re-pack fp32 torch-layout parameters (device, state_dict order) into the kernel image: a 4-KB header (the list of
+ * weight blocks in consumption order, the fp32 output layer, for the modular actor the fp32 first layer of the
+ * integrator branch) followed by the fp16 weight blocks (<= 16 KB each) pre-tiled in the tcgen05 shared-memory operand
+ * layout, so that one cp.async.bulk (TMA) copy brings a ready-to-use B operand.  First layers are stored as hi + lo
+ * fp16 parts ([W_hi | W_hi | W_lo | b_hi b_lo] against [in_hi | in_lo | in_hi | 1 1]): fp32-grade products on the
+ * tensor core; hidden-layer biases as [b_hi b_lo 0 ...] blocks against a constant ones operand. */
 int pime_actor_pack(const pime_actor_config *cfg, const float *params, void *pack, void *stream);
 
 /* a_avg[i] = net(obs[i,:])  (pre-tanh, pre-prior; get_action_noise net_residual.py:172-175 / :51-53).
