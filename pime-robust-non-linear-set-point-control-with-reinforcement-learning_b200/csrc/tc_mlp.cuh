@@ -632,17 +632,13 @@ template <int KIND, int H> struct Engine {
 #pragma unroll
             for (int j = JB; j < JE; ++j) {
                 const int cur = (j - JB) & 1;
-                // The two warps that share a scheduler (half 0 / half 1 of the same rows) run this loop in opposite
-                // phase -- half 0 activates piece j+1 and then emits piece j, half 1 emits first -- so that one of them
-                // is always feeding the MUFU pipe while the other packs and stores.
-                if (half) store_piece(abuf, row, half, j, x[cur]);
-                if (j + 1 < JE) {
+                if (j + 1 < JE) {   // activation of the next piece first: its MUFU work overlaps the stores below
                     tmem_wait_ld();
                     if (j + 2 < JE) tmem_ld16_issue(taddr + (j + 2) * 32, v[cur]);
 #pragma unroll
                     for (int e = 0; e < 16; ++e) x[cur ^ 1][e] = act_pinned<G::kRelu>(v[cur ^ 1][e]);
                 }
-                if (!half) store_piece(abuf, row, half, j, x[cur]);
+                store_piece(abuf, row, half, j, x[cur]);
             }
         }
     }
@@ -666,9 +662,8 @@ template <int KIND, int H> struct Engine {
 #pragma unroll
             for (int j = JB; j < JE; ++j) {
                 const int cur = (j - JB) & 1;
-                if (half) store_piece(abuf, row, half, j, x[cur]);    // opposite phase of the two halves, see epilogue()
                 if (j + 1 < JE) piece(j + 1, x[cur ^ 1]);
-                if (!half) store_piece(abuf, row, half, j, x[cur]);
+                store_piece(abuf, row, half, j, x[cur]);
             }
         }
     }
