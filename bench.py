@@ -47,7 +47,7 @@ WORKLOADS = {
 FLOPS_PER_STEP = {("modular", 256, 4): 264704, ("modular", 128, 3): 66560, ("plain", 256, 30): 278016}  # 2 x weights, SURVEY 8a d4/d5
 TANH_PER_STEP = {("modular", 256, 4): 1025, ("modular", 128, 3): 513, ("plain", 256, 30): 769}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (ncu --set full), keyed by (workload, envs, T); see profiles/
-NCU_DRAM_BYTES_PER_LAUNCH = {("wt", 1 << 20, 200): 6.7759e9}   # profiles/r01_ncu_summary.md (algorithmic: 6.71e9 replay rows)
+NCU_DRAM_BYTES_PER_LAUNCH = {("wt", 1 << 20, 200): 6.7561e9}   # profiles/r01_ncu_summary.md (algorithmic: 6.71e9 replay rows)
 NCU_DRAM_BYTES_STEP = {"wt": 2.1359e9}   # wt_step_kernel<float>, 2^25 envs (algorithmic 1.913e9 + 8 B/env ep_return)
 WT_STEP_BYTES_F32 = 57   # 36 B read + 21 B written per env-step, SoA fp32
 PH_STEP_BYTES_F32 = 53
