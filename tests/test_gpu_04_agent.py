@@ -219,3 +219,20 @@ def test_cuda_graph_minibatch_step_is_transparent():
         assert finals[mode][1] < finals[mode][0]
         assert (agent._graph is not None) == mode
     assert abs(finals[True][1] - finals[False][1]) <= 0.25 * abs(finals[False][1])
+
+
+def test_examples_train_py_runs_the_reference_command_line(tmp_path):
+    """examples/train.py = the reference's train.py command line on this stack (run_ph_changing.sh shrunk)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "examples", "train.py"), "--fix_K", "--algo", "ResidualIntegratorModularPPO",
+           "--env", PH, "--net_dim", "32", "--target_step", "1600", "--batch_size", "256", "--repeat_times", "2",
+           "--lambda_gae_adv", "0.99", "--ratio_clip", "0.2", "--gamma", "0.98", "--break_step", "4800", "--eval_times1", "8",
+           "--eval_times2", "8", "--eval_gap", "1", "--num_envs", "32", "--out", str(tmp_path)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    found = [os.path.join(dp, f) for dp, _, fn in os.walk(tmp_path) for f in fn]
+    assert any(f.endswith("final_model/actor.pth") for f in found) and any(f.endswith("final_model/staircase.npz") for f in found)
+    z = np.load([f for f in found if f.endswith("final_model/staircase.npz")][0])
+    assert z["agent.ys"].shape == (250, 32) and z["linear.ys"].shape == (250, 32) and np.isfinite(z["agent.totals"]).all()
