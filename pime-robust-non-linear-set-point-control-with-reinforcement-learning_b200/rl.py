@@ -299,6 +299,7 @@ class AgentPPO:
         self._graph = None
         self.use_cuda_graph = True      # record the minibatch step into a CUDA graph when it is launch bound
         self.graph_max_batch = 8192
+        self.graph_steps = 4            # minibatch steps per recorded graph
 
     # ---- construction
     def _make_actor(self, net_dim, state_dim, action_dim, **kw):
@@ -317,9 +318,10 @@ class AgentPPO:
 
     def _new_optimizer(self):
         # capturable: the minibatch step can be recorded into a CUDA graph (same arithmetic as the eager step)
+        on_gpu = self.device is not None and self.device.type == "cuda"
         self.optimizer = torch.optim.Adam([{"params": self.act.parameters(), "lr": self.learning_rate},
                                            {"params": self.cri.parameters(), "lr": self.learning_rate}],
-                                          capturable=self.device is not None and self.device.type == "cuda")
+                                          capturable=on_gpu, fused=True if on_gpu else None)   # one Adam kernel per step
         self._graph = None
 
     def init_actor_zero(self):
@@ -469,16 +471,26 @@ class AgentPPO:
         sums = torch.zeros(4, device=self.device)
         last = torch.zeros(4, device=self.device)
         use_graph = self.use_cuda_graph and iters >= 8 and batch_size <= self.graph_max_batch and not _dist_on()
+        done = 0
         if use_graph:
-            g = self._graphed_step(minibatch, data, buf_len, batch_size)
-            for _ in range(iters):
+            G = self.graph_steps
+
+            def several(src, out):   # G consecutive minibatch steps per recorded graph; out = (sum of the G loss vectors, last)
+                out[:4].zero_()
+                for _ in range(G):
+                    minibatch(src, out[4:])
+                    out[:4] += out[4:]
+
+            g = self._graphed_step(several, data, buf_len, batch_size)
+            for _ in range(iters // G):
                 g.replay()
-                sums += self._graph["out"]
-            last = self._graph["out"].clone()
-        else:
-            for _ in range(iters):
-                minibatch(data, last)
-                sums += last
+                sums += self._graph["out"][:4]
+            done = (iters // G) * G
+            if done:
+                last = self._graph["out"][4:].clone()
+        for _ in range(iters - done):
+            minibatch(data, last)
+            sums += last
         self._n_updates += int(repeat_times)
         if iters:
             u, a, c, e = (sums / iters).tolist()
@@ -493,10 +505,10 @@ class AgentPPO:
         """One PPO minibatch (index draw, gather, forward, backward, Adam) recorded ONCE into a CUDA graph and replayed:
         the reference's configurations (batch 128-512) are launch-latency bound (~60 small kernels per minibatch).
         The graph reads static copies of the buffer tensors; it is re-recorded when a shape changes."""
-        key = (buf_len, batch_size, tuple(t.shape for t in data))
+        key = (buf_len, batch_size, self.graph_steps, tuple(t.shape for t in data))
         if self._graph is None or self._graph["key"] != key:
             static = tuple(torch.empty_like(t) for t in data)
-            out = torch.zeros(4, device=self.device)
+            out = torch.zeros(8, device=self.device)
             for s, t in zip(static, data):
                 s.copy_(t)
             # snapshot: the warm-up iterations and the capture itself must not change the training state; everything is
