@@ -3,31 +3,35 @@
 // M=128 rows of every tcgen05.mma = the 128 TMEM lanes.  The CTA is a pipeline of four roles connected by mbarriers only:
 //
 //   warps 8-11  (128 threads) : owners.  Thread r owns env r of BOTH groups end to end (plant state in registers):
-//                               observation -> fp16 first-layer operand, later net(obs) from TMEM -> action -> plant step.
-//                               While the workers run the network of one group the owners step the plant of the other.
-//   warps 0-7   (256 threads) : workers.  Two threads per row (even / odd 32-column chunks): the layer epilogues
-//                               TMEM -> regs -> tanh/relu -> fp16 A operand of the next layer, signalled PER CHUNK so
-//                               that the next layer's MMAs run behind the epilogue that feeds them.
-//   warp 12, lane 0           : MMA issuer.  Interprets the block program of the pack: tcgen05.mma.cta_group::1.kind::f16
-//                               (M=128, N<=128, K=16), accumulators ping-pong between two TMEM buffers Da / Db.
-//   warp 13, lane 0           : TMA producer.  cp.async.bulk streams the pre-tiled fp16 weight blocks (<= 8 KB) from
-//                               the L2-resident pack through a deep shared-memory ring (up to 128 KB in flight).
+//                               observation -> first-layer operand, later net(obs) from shared memory -> action -> plant
+//                               step.  While the workers run the network of one group the owners step the plant of the other.
+//   warps 0-7   (256 threads) : workers.  Two threads per row (16 columns each of every 32-column piece): the layer
+//                               epilogues TMEM -> regs -> tanh/relu -> fp16 A operand of the next layer, one barrier
+//                               arrive per 64-column chunk so that the next layer's MMAs run behind the epilogue that
+//                               feeds them.
+//   warp 12 (converged, one   : MMA issuer.  A static program of tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=256, K=16)
+//            elected lane)      per streamed weight block; accumulators in two TMEM buffers Da / Db.
+//   warp 13, lane 0           : TMA producer.  cp.async.bulk streams the pre-tiled fp16 weight blocks (<= 16 KB) from
+//                               the L2-resident pack through a shared-memory ring.
 //
-// EVERY layer runs on the tensor core, so that a worker spends ~1.7 instructions per hidden activation
-// (tcgen05.ld/32 + MUFU.TANH + F2FP/2 + STS/8) and the kernel is bound by the MUFU pipe (16 tanh/clk/SM):
-//   * first layers (1..31 inputs): the fp32 observation is split into fp16 hi + lo parts and the fp32 weight into
+// The layers run on the tensor core, so that a worker spends ~1.7 instructions per hidden activation
+// (tcgen05.ld/16 + MUFU.TANH + F2FP/2 + STS/8) and the kernel is bound by the MUFU pipe (16 tanh/clk/SM):
+//   * first layers (2..32 inputs): the fp32 observation is split into fp16 hi + lo parts and the fp32 weight into
 //     hi + lo parts, A = [in_hi | in_lo | in_hi | 1 1], B = [W_hi | W_hi | W_lo | b_hi b_lo]  (3 terms, ~2^-22
-//     relative: an fp32-grade first layer; 2 terms when 3S+2 > 32);
+//     relative: an fp32-grade first layer; 2 terms for more than 10 inputs); the one-input first layer of the modular
+//     actor's integrator branch is w * I + b on the CUDA cores (fp32), which frees it from TMEM and the tensor pipe;
 //   * hidden layers: A = fp16 activations written by the previous epilogue, B = fp16 weights; the bias enters
 //     through one extra K=16 MMA against a constant "ones" operand, B = [b_hi b_lo 0 ...];
 //   * output layer Linear(H -> 1): an fp32 dot product inside the last epilogue (FMA pipe, idle otherwise); the two
 //     column halves of a row meet in shared memory, where the row's owner picks net(obs) up.
 //
 // Layers (reference elegantrl/net_residual.py), Da = TMEM columns [0,H), Db = [H,2H):
-//   modular (:138-205): P0 integrator_net.0 -> Da (issued while the previous pass finishes on Db), other_net.0 -> Db;
-//                       P1 integrator_net.2 -> Da[0:H/2] (behind the epilogue of Da);  P2 other_net.2 -> Da[H/2:H]
-//                       (behind the epilogue of Db);  P3 net.0 on cat' = Da = [integrator | other] -> Db (input columns
-//                       rotated in the pack);  net.2 in the epilogue of Db.
+//   modular (:138-205): software-pipelined over passes, two A tiles / barrier sets used alternately by consecutive
+//                       epilogues (see Engine::worker_loop):  E1 tanh(integrator_net.0) on the CUDA cores, wrapped around
+//                       the previous pass's last epilogue;  P1 integrator_net.2 -> Da[0:H/2];  other_net.0 -> Db as soon
+//                       as the previous pass has released Db;  E2 tanh(Db);  P2 other_net.2 -> Da[H/2:H];  E3 tanh(cat'),
+//                       cat' = Da = [integrator | other] (net.0's input columns are rotated in the pack);  P3 net.0 -> Db;
+//                       E4 tanh(Db) . net.2 during the NEXT pass's E1.
 //   plain (:6-66) / CriticAdv (net.py:274-277): P0 net.0 -> X, P1 net.2 -> Y, P2 net.4 -> X, net.6 in the epilogue of X,
 //                       with (X, Y) = (Da, Db) on even passes and (Db, Da) on odd ones, so that P0 never waits.
 #pragma once
