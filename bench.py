@@ -48,7 +48,7 @@ FLOPS_PER_STEP = {("modular", 256, 4): 264704, ("modular", 128, 3): 66560, ("pla
 TANH_PER_STEP = {("modular", 256, 4): 1025, ("modular", 128, 3): 513, ("plain", 256, 30): 769}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (ncu --set full), keyed by (workload, envs, T); see profiles/
 NCU_DRAM_BYTES_PER_LAUNCH = {("wt", 1 << 20, 200): 6.7561e9}   # profiles/r01_ncu_summary.md (algorithmic: 6.71e9 replay rows)
-NCU_DRAM_BYTES_STEP = {"wt": 2.1359e9}   # wt_step_kernel<float>, 2^25 envs (algorithmic 1.913e9 + 8 B/env ep_return)
+NCU_DRAM_BYTES_STEP = {"wt": 1.8720e9, "ph": 1.7354e9}   # *_step_kernel<float>, 2^25 envs (algorithmic 1.913e9 / 1.778e9)
 WT_STEP_BYTES_F32 = 57   # 36 B read + 21 B written per env-step, SoA fp32
 PH_STEP_BYTES_F32 = 53
 
@@ -405,14 +405,16 @@ def aux_step_rooflines(V, pk):
         import pime_b200._lib as L
         reward = torch.empty(n, dtype=torch.float32, device="cuda")
         done = torch.empty(n, dtype=torch.uint8, device="cuda")
+        st = type(env._st).from_buffer_copy(env._st)
+        st.ep_return = None   # the gym-API step of the reference keeps no running return: the 57 / 53 B of SURVEY 8d
 
         def launch():
             if name == "wt":
-                L.check(L.lib().pime_wt_step_f32(C.byref(env.cfg), C.c_int64(n), C.byref(env._st), L.ptr(act), None, None,
+                L.check(L.lib().pime_wt_step_f32(C.byref(env.cfg), C.c_int64(n), C.byref(st), L.ptr(act), None, None,
                                                  C.c_uint64(0), C.c_uint64(0), C.c_uint32(0), None, L.ptr(reward), L.ptr(done),
                                                  L.stream_ptr()))
             else:
-                L.check(L.lib().pime_ph_step_f32(C.byref(env.cfg), L.ptr(env.table), C.c_int64(n), C.byref(env._st), L.ptr(act),
+                L.check(L.lib().pime_ph_step_f32(C.byref(env.cfg), L.ptr(env.table), C.c_int64(n), C.byref(st), L.ptr(act),
                                                  None, L.ptr(reward), L.ptr(done), L.ptr(env.status), L.stream_ptr()))
         for _ in range(3):
             launch()
