@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PIME_B200_ABI_VERSION 1
+#define PIME_B200_ABI_VERSION 2
 
 enum {
     PIME_OK = 0,
@@ -66,7 +66,9 @@ typedef struct pime_wt_config {
     int32_t reward_type;         /* PIME_REWARD_*  (:486-514)                                     */
     int32_t obs_mode;            /* PIME_WT_OBS_*                                                 */
     int32_t num_stack;           /* frames in PIME_WT_OBS_STACKING (1, 4, 10), else ignored       */
-    int32_t reserved0;
+    int32_t reset_from_last_state; /* 1: reset() restarts from the levels of the last finished episode
+                                    (|N(0,1)|*0.1 before the first one) instead of U(h_lo,h_hi) (:904-912);
+                                    needs state.last_h1/last_h2.  0 at every registered id.       */
     double z1;                   /* 1.0                                                           */
     double distance_threshold;   /* 0.05 (sparse reward)                                          */
     double integral_max;         /* 25.0 (:731-733)                                               */
@@ -87,6 +89,8 @@ typedef struct pime_wt_state {
     uint32_t *episode;    /* number of resets so far (RNG tick)                                          */
     void *ep_return;      /* running sum of rewards of the current episode                               */
     void *frames;         /* PIME_WT_OBS_STACKING: [3*num_stack][n] (component-major), else NULL         */
+    void *last_h1, *last_h2; /* levels at the last `done` (:819-821); NaN = None.  Required when
+                                cfg.reset_from_last_state, else may be NULL                              */
 } pime_wt_state;
 
 void pime_wt_default_config(pime_wt_config *cfg); /* registered ...Integrator-SquareDistance-v2 values */
@@ -120,6 +124,9 @@ typedef struct pime_ph_config {
     int32_t integrator_mode;    /* PIME_PH_*                                                             */
     int32_t max_episode_steps;  /* 50, gym TimeLimit (gym_control/__init__.py:6)                         */
     int32_t table_len;          /* len(MHCl) = 100000 (gym_control/__init__.py:12)                       */
+    int32_t reset_from_last_state; /* 1: reset() keeps the state of the last finished episode (ph.py:417-420,
+                                    :345-346); needs state.last_x.  0 at every registered id.            */
+    int32_t reserved0;
     double act_low, act_high;   /* 0.0, 1.5 (ph.py:146-147)                                              */
     double sample_t;            /* 20 (ph.py:40)                                                         */
     double mhcl_step;           /* 1e-5                                                                  */
@@ -138,6 +145,8 @@ typedef struct pime_ph_state {
     int32_t *t;
     uint32_t *episode;
     void *ep_return;
+    void *last_x;         /* state at the last time-limit step (ph.py:345-346); NaN = None.  Required when
+                             cfg.reset_from_last_state, else may be NULL                                 */
 } pime_ph_state;
 
 void pime_ph_default_config(pime_ph_config *cfg); /* registered PH1D...Integrator-SqaureDistance-v35 values */

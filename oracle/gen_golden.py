@@ -423,6 +423,63 @@ def gen_ppo(ref, rng):
     np.savez_compressed(os.path.join(OUT, "ppo.npz"), **out)
 
 
+def gen_last_state(ref):
+    """reset_from_last_state=True (nonlinear_watertank.py:904-910, :819-821; ph.py:417-420, :345-346): a scripted
+    sequence of reset / step calls on the reference; every row records the env after the call."""
+    out = {}
+    np.random.seed(4242)
+    env = ref.gym.make(WT_INT, reset_from_last_state=True, max_step=6, noise_scale=0.0, reward_type="distance").unwrapped
+    rows, script = [], []
+
+    def rec(kind, arg=0.0):
+        script.append((kind, arg))
+        rows.append([env.h1, env.h2, env.r, env.integrator, env._episode_steps,
+                     np.nan if env.last_h1 is None else env.last_h1, np.nan if env.last_h2 is None else env.last_h2,
+                     env.a1, env.a2, env.Kp])
+
+    env.reset(); rec(0)                                   # last is None -> |randn| * 0.1
+    first = (env.h1, env.h2)
+    assert 0 <= first[0] < 1 and 0 <= first[1] < 1
+    acts = [0.9, 0.5, -0.2, 0.7, 1.0, 0.1, -0.6, 0.3]
+    for ep in range(2):                                   # two full episodes: done at t = 6 records the levels
+        for k in range(6):
+            _, _, done, _ = env.step(np.array([acts[(k + ep) % 8]])); rec(1, acts[(k + ep) % 8])
+        assert done
+        env.reset(); rec(0)                               # restarts from the recorded levels
+    for k in range(3):                                    # reset in mid-episode goes back to the levels at the last done
+        env.step(np.array([acts[k]])); rec(1, acts[k])
+    env.reset(); rec(0)
+    env.if_reset_all = False                              # README.md:27-33
+    for k in range(6):
+        env.step(np.array([0.4])); rec(1, 0.4)
+    env.reset(); rec(0)                                   # reset_r path (:920-926)
+    out["wt_rows"] = np.asarray(rows, np.float64)
+    out["wt_script"] = np.asarray(script, np.float64)
+
+    env = ref.gym.make(PH_INT, reset_from_last_state=True)
+    u = env.unwrapped
+    rows, script = [], []
+
+    def recp(kind, arg=0.0, done=False):
+        script.append((kind, arg))
+        rows.append([scal(u.state), scal(u.y), u.r, scal(u.integrator), u._episode_steps,
+                     np.nan if u.last_state is None else scal(u.last_state), u.qww_V, u.qc_V, float(done)])
+
+    env.reset(); recp(0)
+    for ep in range(2):
+        for k in range(50):
+            a = 0.8 * np.sin(0.37 * k + ep)
+            _, _, done, _ = env.step(np.array([a])); recp(1, a, done)
+        assert done
+        env.reset(); recp(0)
+    for k in range(5):
+        env.step(np.array([0.25])); recp(1, 0.25)
+    env.reset(); recp(0)
+    out["ph_rows"] = np.asarray(rows, np.float64)
+    out["ph_script"] = np.asarray(script, np.float64)
+    np.savez_compressed(os.path.join(OUT, "last_state.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
@@ -434,6 +491,7 @@ def main():
     gen_actor(ref, rng)
     gen_explore(ref, rng, table)
     gen_ppo(ref, np.random.default_rng(20261019))
+    gen_last_state(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -23,7 +23,7 @@ vp = C.c_void_p
 class WtConfig(C.Structure):
     _fields_ = [("A1", C.c_double), ("A2", C.c_double), ("G", C.c_double), ("sample_t", C.c_double),
                 ("n_discrete", C.c_int32), ("max_step", C.c_int32), ("P_max_action", C.c_double),
-                ("reward_type", C.c_int32), ("obs_mode", C.c_int32), ("num_stack", C.c_int32), ("reserved0", C.c_int32),
+                ("reward_type", C.c_int32), ("obs_mode", C.c_int32), ("num_stack", C.c_int32), ("reset_from_last_state", C.c_int32),
                 ("z1", C.c_double), ("distance_threshold", C.c_double), ("integral_max", C.c_double),
                 ("integral_punish", C.c_double), ("noise_scale", C.c_double),
                 ("a1_lo", C.c_double), ("a1_hi", C.c_double), ("a2_lo", C.c_double), ("a2_hi", C.c_double),
@@ -33,12 +33,13 @@ class WtConfig(C.Structure):
 
 class WtState(C.Structure):
     _fields_ = [("h1", vp), ("h2", vp), ("r", vp), ("I", vp), ("a1", vp), ("a2", vp), ("Kp", vp), ("t", vp),
-                ("episode", vp), ("ep_return", vp), ("frames", vp)]
+                ("episode", vp), ("ep_return", vp), ("frames", vp), ("last_h1", vp), ("last_h2", vp)]
 
 
 class PhConfig(C.Structure):
     _fields_ = [("reward_type", C.c_int32), ("integrator_mode", C.c_int32), ("max_episode_steps", C.c_int32),
-                ("table_len", C.c_int32), ("act_low", C.c_double), ("act_high", C.c_double), ("sample_t", C.c_double),
+                ("table_len", C.c_int32), ("reset_from_last_state", C.c_int32), ("reserved0", C.c_int32),
+                ("act_low", C.c_double), ("act_high", C.c_double), ("sample_t", C.c_double),
                 ("mhcl_step", C.c_double), ("distance_threshold", C.c_double), ("integral_max", C.c_double),
                 ("integral_punish", C.c_double), ("action_punishment", C.c_double),
                 ("kw", C.c_double), ("kchem", C.c_double), ("ka", C.c_double), ("MNaOH", C.c_double), ("MHA", C.c_double),
@@ -48,7 +49,7 @@ class PhConfig(C.Structure):
 
 class PhState(C.Structure):
     _fields_ = [("x", vp), ("y", vp), ("r", vp), ("I", vp), ("A", vp), ("B", vp), ("C", vp), ("qww_V", vp), ("qc_V", vp),
-                ("t", vp), ("episode", vp), ("ep_return", vp)]
+                ("t", vp), ("episode", vp), ("ep_return", vp), ("last_x", vp)]
 
 
 class ActorConfig(C.Structure):

@@ -129,6 +129,7 @@ template <> struct Num<float> {
 
 template <typename T> __device__ __forceinline__ T clip_lo0(T v) { return v < (T)0 ? (T)0 : v; }
 
+template <typename T> __device__ __forceinline__ T nan_of() { return (T)__int_as_float(0x7fc00000); }
 template <typename T> __device__ __forceinline__ T clampT(T v, T lo, T hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // reward of |achieved - goal| (nonlinear_watertank.py:486-514, ph.py:202-225)

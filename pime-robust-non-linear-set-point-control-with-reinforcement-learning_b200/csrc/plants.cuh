@@ -12,7 +12,7 @@ template <typename T> struct WtConst {
     // f32 fast path: sqrt(2G)*dt/A folded once per launch
     T sq2G_dt_over_A1, sq2G_dt_over_A2, dt_over_A1;
     T a1_lo, a1_w, a2_lo, a2_w, Kp_lo, Kp_w, h_lo, h_w, r_lo, r_w;
-    int n_discrete, max_step, reward_type, obs_mode, num_stack;
+    int n_discrete, max_step, reward_type, obs_mode, num_stack, from_last;
 };
 
 template <typename T> inline WtConst<T> make_wt_const(const pime_wt_config &c) {
@@ -33,7 +33,7 @@ template <typename T> inline WtConst<T> make_wt_const(const pime_wt_config &c) {
     k.h_lo = (T)c.h_lo; k.h_w = (T)(c.h_hi - c.h_lo);
     k.r_lo = (T)c.r_lo; k.r_w = (T)(c.r_hi - c.r_lo);
     k.n_discrete = c.n_discrete; k.max_step = c.max_step; k.reward_type = c.reward_type;
-    k.obs_mode = c.obs_mode; k.num_stack = c.num_stack;
+    k.obs_mode = c.obs_mode; k.num_stack = c.num_stack; k.from_last = c.reset_from_last_state;
     return k;
 }
 
@@ -111,11 +111,25 @@ template <typename T> __device__ __forceinline__ void wt_reset(const WtConst<T> 
     e.I = (T)0;
 }
 
+// reset_from_last_state=True (:904-910): the levels of the last finished episode, or |N(0,1)|*0.1 before the first one
+// (last1 is NaN = None).  The two normals are the Box-Muller pair of the uniforms that would have drawn h1, h2.
+template <typename T> __device__ __forceinline__ void wt_reset_levels_from_last(WtEnv<T> &e, const double u[6], T last1, T last2) {
+    if (last1 == last1) {
+        e.h1 = last1;
+        e.h2 = last2;
+    } else {
+        double rad = sqrt(-2.0 * log1p(-u[3])), sn, cs;
+        sincospi(2.0 * u[4], &sn, &cs);
+        e.h1 = (T)(fabs(rad * cs) * 0.1);
+        e.h2 = (T)(fabs(rad * sn) * 0.1);
+    }
+}
+
 // ============================================================================================== pH
 template <typename T> struct PhConst {
     T act_low, act_w, thr, Imax, Ipunish, act_punish, sample_t;
     T qww_lo, qww_w, qc_lo, qc_w, x_lo, x_w, r_lo, r_w;
-    int reward_type, integrator_mode, max_episode_steps, table_len;
+    int reward_type, integrator_mode, max_episode_steps, table_len, from_last;
 };
 
 template <typename T> inline PhConst<T> make_ph_const(const pime_ph_config &c) {
@@ -128,7 +142,7 @@ template <typename T> inline PhConst<T> make_ph_const(const pime_ph_config &c) {
     k.x_lo = (T)c.x_lo; k.x_w = (T)(c.x_hi - c.x_lo);
     k.r_lo = (T)c.r_lo; k.r_w = (T)(c.r_hi - c.r_lo);
     k.reward_type = c.reward_type; k.integrator_mode = c.integrator_mode;
-    k.max_episode_steps = c.max_episode_steps; k.table_len = c.table_len;
+    k.max_episode_steps = c.max_episode_steps; k.table_len = c.table_len; k.from_last = c.reset_from_last_state;
     return k;
 }
 
@@ -188,15 +202,16 @@ template <typename T> __device__ __forceinline__ void ph_update_system(T sample_
     C = qc;
 }
 
+// last_x: the state kept by reset_from_last_state=True (:417-418, :430-431); NaN = None / flag off.
 template <typename T>
 __device__ __forceinline__ bool ph_reset(const PhConst<T> &c, const T *__restrict__ table, PhEnv<T> &e, T &qww, T &qc,
-                                         const double u[6], bool resample) {
+                                         const double u[6], bool resample, T last_x) {
     if (resample) {  // sample_parameters (:409-410) + update_system (:414)
         qww = (T)((double)c.qww_lo + (double)c.qww_w * u[0]);
         qc = (T)((double)c.qc_lo + (double)c.qc_w * u[1]);
         ph_update_system<T>(c.sample_t, qww, qc, e.A, e.B, e.C);
     }
-    e.x = (T)((double)c.x_lo + (double)c.x_w * u[2]);   // :420
+    e.x = last_x == last_x ? last_x : (T)((double)c.x_lo + (double)c.x_w * u[2]);   // :417-420
     bool ok = ph_lookup(table, c.table_len, e.C, e.x, e.y); // :422
     e.t = 0;
     e.r = (T)((double)c.r_lo + (double)c.r_w * u[3]);   // :424

@@ -36,7 +36,7 @@ constexpr int kMaxFrames = 30;
 template <typename T, bool STACK> struct WtGlue {
     using Real = T;
     WtConst<T> c;
-    T *h1, *h2, *r, *I, *a1, *a2, *Kp, *ep_return, *frames;
+    T *h1, *h2, *r, *I, *a1, *a2, *Kp, *ep_return, *frames, *last_h1, *last_h2;
     int32_t *t;
     uint32_t *episode;
 
@@ -99,10 +99,17 @@ template <typename T, bool STACK> struct WtGlue {
         return true;
     }
     __device__ __forceinline__ T tracking_error(const Env &v) const { return Num<T>::abs(v.e.r - v.e.h2); }
+    // `done` bookkeeping of reset_from_last_state (:819-821)
+    __device__ __forceinline__ void record_done(const Env &v, int64_t i) const {
+        if (last_h1) { last_h1[i] = v.e.h1; last_h2[i] = v.e.h2; }
+    }
+    // the in-kernel reset always follows a `done`, so "the levels of the last finished episode" are the current ones
     __device__ __forceinline__ bool reset(Env &v, uint64_t seed, uint64_t index) const {
         double u[6];
         reset_uniforms(seed, index, v.episode, u);
+        const T k1 = v.e.h1, k2 = v.e.h2;
         wt_reset(c, v.e, u, true);
+        if (c.from_last) { v.e.h1 = k1; v.e.h2 = k2; }
         v.episode += 1;
         if constexpr (STACK) {
             const int m = 3 * c.num_stack;
@@ -118,7 +125,7 @@ template <typename T> struct PhGlue {
     using Real = T;
     PhConst<T> c;
     const T *table;
-    T *x, *y, *r, *I, *A, *B, *C, *qww, *qc, *ep_return;
+    T *x, *y, *r, *I, *A, *B, *C, *qww, *qc, *ep_return, *last_x;
     int32_t *t;
     uint32_t *episode;
 
@@ -155,10 +162,13 @@ template <typename T> struct PhGlue {
         return ph_advance(c, table, v.e, action, rew, done);
     }
     __device__ __forceinline__ T tracking_error(const Env &v) const { return Num<T>::abs(v.e.r - v.e.y); }
+    __device__ __forceinline__ void record_done(const Env &v, int64_t i) const {   // ph.py:345-346
+        if (last_x) last_x[i] = v.e.x;
+    }
     __device__ __forceinline__ bool reset(Env &v, uint64_t seed, uint64_t index) const {
         double u[6];
         reset_uniforms(seed, index, v.episode, u);
-        bool ok = ph_reset(c, table, v.e, v.qww, v.qc, u, true);
+        bool ok = ph_reset(c, table, v.e, v.qww, v.qc, u, true, c.from_last ? v.e.x : nan_of<T>());
         v.episode += 1;
         return ok;
     }
@@ -237,6 +247,7 @@ template <typename Plant> struct Stepper {
             s_rew += (double)rew;
             s_steps += 1.0;
             if (done) {
+                plant.record_done(env, ii);
                 s_ret += (double)env.ret;
                 s_ret2 += (double)env.ret * (double)env.ret;
                 s_cnt += 1.0;

@@ -13,6 +13,7 @@ int ph_rollout_impl(const pime_ph_config *cfg, const T *table, int64_t n, const 
                  "null state array");
     PIME_REQUIRE(cfg->integrator_mode >= 0 && cfg->integrator_mode <= 2, "integrator_mode");
     PIME_REQUIRE(cfg->integrator_mode == PIME_PH_NO_INTEGRATOR || st->I, "integrator array missing");
+    PIME_REQUIRE(!cfg->reset_from_last_state || st->last_x, "reset_from_last_state needs last_x");
     const int S = cfg->integrator_mode == PIME_PH_NO_INTEGRATOR ? 2 : 3;
     RolloutParams rp;
     tc::PackLayout L;
@@ -24,7 +25,7 @@ int ph_rollout_impl(const pime_ph_config *cfg, const T *table, int64_t n, const 
     g.table = table;
     g.x = (T *)st->x; g.y = (T *)st->y; g.r = (T *)st->r; g.I = (T *)st->I;
     g.A = (T *)st->A; g.B = (T *)st->B; g.C = (T *)st->C; g.qww = (T *)st->qww_V; g.qc = (T *)st->qc_V;
-    g.ep_return = (T *)st->ep_return; g.t = st->t; g.episode = st->episode;
+    g.ep_return = (T *)st->ep_return; g.last_x = (T *)st->last_x; g.t = st->t; g.episode = st->episode;
     cudaStream_t s = (cudaStream_t)stream;
     if (!rp.has_actor) return launch_rollout_prior<PhGlue<T>>(g, rp, s);
     if (args->actor->kind == PIME_ACTOR_MODULAR) {

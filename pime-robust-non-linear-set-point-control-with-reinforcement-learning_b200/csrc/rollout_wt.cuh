@@ -13,6 +13,7 @@ int wt_rollout_impl(const pime_wt_config *cfg, int64_t n, const pime_wt_state *s
     PIME_REQUIRE(cfg->obs_mode != PIME_WT_OBS_INTEGRATOR || st->I, "integrator array missing");
     PIME_REQUIRE(cfg->obs_mode != PIME_WT_OBS_STACKING || (st->frames && cfg->num_stack >= 1 && cfg->num_stack <= 10),
                  "stacking needs frames and 1 <= num_stack <= 10");
+    PIME_REQUIRE(!cfg->reset_from_last_state || (st->last_h1 && st->last_h2), "reset_from_last_state needs last_h1/last_h2");
     const int S = cfg->obs_mode == PIME_WT_OBS_GOAL ? 3 : (cfg->obs_mode == PIME_WT_OBS_INTEGRATOR ? 4 : 3 * cfg->num_stack);
     RolloutParams rp;
     tc::PackLayout L;
@@ -25,6 +26,7 @@ int wt_rollout_impl(const pime_wt_config *cfg, int64_t n, const pime_wt_state *s
         g.h1 = (T *)st->h1; g.h2 = (T *)st->h2; g.r = (T *)st->r; g.I = (T *)st->I;
         g.a1 = (T *)st->a1; g.a2 = (T *)st->a2; g.Kp = (T *)st->Kp;
         g.ep_return = (T *)st->ep_return; g.frames = (T *)st->frames; g.t = st->t; g.episode = st->episode;
+        g.last_h1 = (T *)st->last_h1; g.last_h2 = (T *)st->last_h2;
     };
     if (cfg->obs_mode == PIME_WT_OBS_STACKING) {   // observation history: plain actor only (the modular one needs the integrator)
         WtGlue<T, true> g;

@@ -9,7 +9,7 @@ constexpr int kBlock = 256;
 
 // ---------------------------------------------------------------------------------------------- water tank
 template <typename T> struct WtPtrs {
-    T *h1, *h2, *r, *I, *a1, *a2, *Kp, *ep_return, *frames;
+    T *h1, *h2, *r, *I, *a1, *a2, *Kp, *ep_return, *frames, *last_h1, *last_h2;
     int32_t *t;
     uint32_t *episode;
 };
@@ -19,6 +19,7 @@ template <typename T> static WtPtrs<T> wt_ptrs(const pime_wt_state *s) {
     p.h1 = (T *)s->h1; p.h2 = (T *)s->h2; p.r = (T *)s->r; p.I = (T *)s->I;
     p.a1 = (T *)s->a1; p.a2 = (T *)s->a2; p.Kp = (T *)s->Kp;
     p.ep_return = (T *)s->ep_return; p.frames = (T *)s->frames;
+    p.last_h1 = (T *)s->last_h1; p.last_h2 = (T *)s->last_h2;
     p.t = s->t; p.episode = s->episode;
     return p;
 }
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(kBlock) wt_step_kernel(WtConst<T> c, int64_t n
         if (p.ep_return) p.ep_return[i] += rew;
         reward[i] = rew;
         done[i] = dn ? 1 : 0;
+        if (dn && p.last_h1) { p.last_h1[i] = e.h1; p.last_h2[i] = e.h2; }                      // :819-821
         wt_write_obs(c, p, e, i, n, obs_out, false);
     }
 }
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(kBlock) wt_reset_kernel(WtConst<T> c, int64_t 
         double u[6];
         reset_uniforms(seed, env_offset + (uint64_t)i, ep, u);
         wt_reset(c, e, u, resample != 0);
+        if (c.from_last) wt_reset_levels_from_last(e, u, p.last_h1[i], p.last_h2[i]);
         p.episode[i] = ep + 1;
         p.a1[i] = e.a1; p.a2[i] = e.a2; p.Kp[i] = e.Kp;
         p.h1[i] = e.h1; p.h2[i] = e.h2; p.r[i] = e.r;
@@ -116,6 +119,7 @@ static int check_wt(const pime_wt_config *cfg, int64_t n, const pime_wt_state *s
     PIME_REQUIRE(cfg->obs_mode != PIME_WT_OBS_STACKING || (st->frames && cfg->num_stack >= 1 && cfg->num_stack <= 10),
                  "stacking needs frames and 1 <= num_stack <= 10");
     PIME_REQUIRE(cfg->n_discrete >= 1 && cfg->reward_type >= 0 && cfg->reward_type <= 2, "n_discrete/reward_type");
+    PIME_REQUIRE(!cfg->reset_from_last_state || (st->last_h1 && st->last_h2), "reset_from_last_state needs last_h1/last_h2");
     return PIME_OK;
 }
 
@@ -149,7 +153,7 @@ static int wt_reset_impl(const pime_wt_config *cfg, int64_t n, const pime_wt_sta
 
 // ---------------------------------------------------------------------------------------------- pH
 template <typename T> struct PhPtrs {
-    T *x, *y, *r, *I, *A, *B, *C, *qww, *qc, *ep_return;
+    T *x, *y, *r, *I, *A, *B, *C, *qww, *qc, *ep_return, *last_x;
     int32_t *t;
     uint32_t *episode;
 };
@@ -158,7 +162,7 @@ template <typename T> static PhPtrs<T> ph_ptrs(const pime_ph_state *s) {
     PhPtrs<T> p;
     p.x = (T *)s->x; p.y = (T *)s->y; p.r = (T *)s->r; p.I = (T *)s->I;
     p.A = (T *)s->A; p.B = (T *)s->B; p.C = (T *)s->C; p.qww = (T *)s->qww_V; p.qc = (T *)s->qc_V;
-    p.ep_return = (T *)s->ep_return; p.t = s->t; p.episode = s->episode;
+    p.ep_return = (T *)s->ep_return; p.last_x = (T *)s->last_x; p.t = s->t; p.episode = s->episode;
     return p;
 }
 
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(kBlock) ph_step_kernel(PhConst<T> c, const T *
         if (p.ep_return) p.ep_return[i] += rew;
         reward[i] = rew;
         done[i] = dn ? 1 : 0;
+        if (dn && p.last_x) p.last_x[i] = e.x;                                                  // :345-346
         ph_write_obs(c, e, i, n, obs_out);
     }
 }
@@ -206,7 +211,7 @@ __global__ void __launch_bounds__(kBlock) ph_reset_kernel(PhConst<T> c, const T 
         uint32_t ep = p.episode[i];
         double u[6];
         reset_uniforms(seed, env_offset + (uint64_t)i, ep, u);
-        bool ok = ph_reset(c, table, e, qww, qc, u, resample != 0);
+        bool ok = ph_reset(c, table, e, qww, qc, u, resample != 0, c.from_last ? p.last_x[i] : nan_of<T>());
         if (!ok && status) atomicMin(status, (int32_t)PIME_ERANGE);
         p.episode[i] = ep + 1;
         p.qww[i] = qww; p.qc[i] = qc;
@@ -272,6 +277,7 @@ static int check_ph(const pime_ph_config *cfg, int64_t n, const pime_ph_state *s
     PIME_REQUIRE(cfg->integrator_mode >= 0 && cfg->integrator_mode <= 2, "integrator_mode");
     PIME_REQUIRE(cfg->integrator_mode == PIME_PH_NO_INTEGRATOR || st->I, "integrator array missing");
     PIME_REQUIRE(cfg->table_len > 1 && cfg->reward_type >= 0 && cfg->reward_type <= 2, "table_len/reward_type");
+    PIME_REQUIRE(!cfg->reset_from_last_state || st->last_x, "reset_from_last_state needs last_x");
     return PIME_OK;
 }
 

@@ -75,6 +75,15 @@ class _DeviceEnv(_EnvBase):
         v = t.detach().cpu().numpy()
         return v[0].item() if self.num_envs == 1 else v.copy()
 
+    def _last(self, name):
+        t = getattr(self.vec, name)
+        if t is None:
+            return None
+        v = self._scalar(t)
+        if self.num_envs == 1:
+            return None if np.isnan(v) else v
+        return v
+
     def seed(self, seed=None):
         """gym seeding API.  The device streams are Philox keyed by (seed, env id, tick); None keeps the current seed."""
         if seed is not None:
@@ -111,8 +120,6 @@ class NonLinearWaterTankChangingParamUniformGoal(_DeviceEnv):
                  num_envs=1, device="cuda", dtype=torch.float64):
         if controller_type != "P":
             raise NotImplementedError("only controller_type='P' (the registered configuration) is implemented")
-        if reset_from_last_state:
-            raise NotImplementedError("reset_from_last_state=True is not implemented (registered configs use False)")
         self.num_envs = int(num_envs)
         self._dtype = dtype   # float64 = the reference's arithmetic (default); float32 = the throughput kernels
         self.a1_range, self.a2_range, self.Kp_range = list(a1), list(a2), list(Kp)
@@ -124,7 +131,7 @@ class NonLinearWaterTankChangingParamUniformGoal(_DeviceEnv):
         self.K, self.L = np.asarray(P_control_K, dtype=np.float64), None
         self.num_stack = int(num_stack)
         self.if_reset_all = True
-        self.reset_from_last_state = False
+        self.reset_from_last_state = bool(reset_from_last_state)   # nonlinear_watertank.py:152, :904-910
         self.m = {"goal": 3, "integrator": 3, "stacking": 3 * self.num_stack}[self._obs_mode]
         self.n = 1
         self._device = device
@@ -149,12 +156,15 @@ class NonLinearWaterTankChangingParamUniformGoal(_DeviceEnv):
 
     def _make_vec(self, seed):
         self.vec = WaterTankVec(self.num_envs, dtype=self._dtype, device=self._device, obs_mode=self._obs_mode,
-                                num_stack=self.num_stack, seed=seed, **self._cfg_kwargs())
+                                num_stack=self.num_stack, seed=seed, reset_from_last_state=self.reset_from_last_state,
+                                **self._cfg_kwargs())
 
     def _clone_vec(self):
         v = WaterTankVec(self.num_envs, dtype=self._dtype, device=self._device, obs_mode=self._obs_mode,
-                         num_stack=self.num_stack, seed=self.vec.seed, env_offset=self.vec.env_offset, **self._cfg_kwargs())
-        for k in ("h1", "h2", "r", "I", "a1", "a2", "Kp", "t", "episode", "ep_return"):
+                         num_stack=self.num_stack, seed=self.vec.seed, env_offset=self.vec.env_offset,
+                         reset_from_last_state=self.reset_from_last_state, **self._cfg_kwargs())
+        for k in ("h1", "h2", "r", "I", "a1", "a2", "Kp", "t", "episode", "ep_return") + (
+                ("last_h1", "last_h2") if self.reset_from_last_state else ()):
             getattr(v, k).copy_(getattr(self.vec, k))
         if v.frames is not None:
             v.frames.copy_(self.vec.frames)
@@ -241,6 +251,9 @@ class NonLinearWaterTankChangingParamUniformGoal(_DeviceEnv):
     state = property(lambda self: self._get_observe())
     _episode_steps = property(lambda self: self._scalar(self.vec.t))
 
+    last_h1 = property(lambda self: self._last("last_h1"))   # None until the first episode ends (:185-186)
+    last_h2 = property(lambda self: self._last("last_h2"))
+
 
 class NonLinearWaterTankChangingParamUniformGoalIntegrator(NonLinearWaterTankChangingParamUniformGoal):
     """Reference nonlinear_watertank.py:828-939 (obs [h1,h2,r,I])."""
@@ -283,8 +296,6 @@ class PH1DChangingParamUniformGoalIntegrator(_DeviceEnv):
                  distance_threshold=0.05, P_control_K=np.array([1, 1]), P_control_L=np.array([-0.4]), action_punishment=0.0,
                  action_change_punishment=0.0, max_episode_steps=200, seed=None, time_limit=None, num_envs=1, device="cuda",
                  dtype=torch.float64):
-        if reset_from_last_state:
-            raise NotImplementedError("reset_from_last_state=True is not implemented (registered configs use False)")
         if action_change_punishment:
             raise NotImplementedError("action_change_punishment != 0 is not implemented (0 at every registered config)")
         self.num_envs = int(num_envs)
@@ -305,7 +316,7 @@ class PH1DChangingParamUniformGoalIntegrator(_DeviceEnv):
         self.action_punishment, self.action_change_punishment = action_punishment, action_change_punishment
         self.low, self.high, self.min_action, self.max_action = 0.0, 1.5, -1, 1
         self.if_reset_all = True
-        self.reset_from_last_state = False
+        self.reset_from_last_state = bool(reset_from_last_state)   # ph.py:101-102, :417-420
         self.m = 3 if self._integrator != "none" else 2
         self.n = 1
         self._device = device
@@ -315,15 +326,16 @@ class PH1DChangingParamUniformGoalIntegrator(_DeviceEnv):
                          kw=kw, kchem=kchem, ka=ka, MNaOH=MNaOH, MHA=MHA, MNH3=MNH3, qww_lo=self.qww_Vrange[0],
                          qww_hi=self.qww_Vrange[1], qc_lo=self.qc_Vrange[0], qc_hi=self.qc_Vrange[1])
         self.vec = PHVec(self.num_envs, dtype=dtype, device=device, integrator=self._integrator,
-                         seed=0 if seed is None else int(seed), **self._cfg)
+                         seed=0 if seed is None else int(seed), reset_from_last_state=self.reset_from_last_state, **self._cfg)
         self.observation_space = Box(low=-np.full(self.m, np.inf), high=np.full(self.m, np.inf), dtype=np.float32)
         self.action_space = Box(low=-np.ones(1), high=np.ones(1), dtype=np.float32)
         self._reset_done = False
 
     def _clone_vec(self):
         v = PHVec(self.num_envs, dtype=self._dtype, device=self._device, integrator=self._integrator, seed=self.vec.seed,
-                  env_offset=self.vec.env_offset, **self._cfg)
-        for k in ("x", "y", "r", "I", "A", "B", "C", "qww_V", "qc_V", "t", "episode", "ep_return"):
+                  env_offset=self.vec.env_offset, reset_from_last_state=self.reset_from_last_state, **self._cfg)
+        for k in ("x", "y", "r", "I", "A", "B", "C", "qww_V", "qc_V", "t", "episode", "ep_return") + (
+                ("last_x",) if self.reset_from_last_state else ()):
             getattr(v, k).copy_(getattr(self.vec, k))
         v.tick = self.vec.tick
         return v
@@ -400,6 +412,7 @@ class PH1DChangingParamUniformGoalIntegrator(_DeviceEnv):
     y = property(lambda self: self._scalar(self.vec.y))
     r = property(lambda self: self._scalar(self.vec.r))
     state = property(lambda self: self._scalar(self.vec.x))
+    last_state = property(lambda self: self._last("last_x"))   # None until an episode reaches the step limit (ph.py:102)
     qww_V = property(lambda self: self._scalar(self.vec.qww_V))
     qc_V = property(lambda self: self._scalar(self.vec.qc_V))
     _episode_steps = property(lambda self: self._scalar(self.vec.t))

@@ -168,19 +168,26 @@ class WaterTankVec(_VecBase):
     OBS = {"goal": L.WT_OBS_GOAL, "integrator": L.WT_OBS_INTEGRATOR, "stacking": L.WT_OBS_STACKING}
 
     def __init__(self, n: int, dtype=torch.float32, device="cuda", obs_mode="integrator", num_stack=0, seed=0, env_offset=0,
-                 **cfg):
+                 reset_from_last_state=False, **cfg):
         self.device = _require_cuda(device)
         self.n, self.dtype, self.seed, self.env_offset = int(n), dtype, int(seed), int(env_offset)
-        self.cfg = L.wt_config(obs_mode=self.OBS[obs_mode], num_stack=int(num_stack), **cfg)
+        self.cfg = L.wt_config(obs_mode=self.OBS[obs_mode], num_stack=int(num_stack),
+                               reset_from_last_state=int(bool(reset_from_last_state)), **cfg)
         self.obs_mode = obs_mode
         self.num_stack = int(num_stack)
         self.state_dim = {"goal": 3, "integrator": 4}.get(obs_mode, 3 * self.num_stack)
         self._alloc(["h1", "h2", "r", "I", "a1", "a2", "Kp"], self.n)
         self.frames = (torch.zeros((3 * self.num_stack, self.n), dtype=dtype, device=self.device)
                        if obs_mode == "stacking" else None)
+        # levels at the last `done` (nonlinear_watertank.py:185-186, :819-821); NaN = None
+        self.last_h1 = self.last_h2 = None
+        if reset_from_last_state:
+            self.last_h1 = torch.full((self.n,), float("nan"), dtype=dtype, device=self.device)
+            self.last_h2 = torch.full((self.n,), float("nan"), dtype=dtype, device=self.device)
         self._st = L.WtState(h1=L.ptr(self.h1), h2=L.ptr(self.h2), r=L.ptr(self.r), I=L.ptr(self.I), a1=L.ptr(self.a1),
                              a2=L.ptr(self.a2), Kp=L.ptr(self.Kp), t=L.ptr(self.t), episode=L.ptr(self.episode),
-                             ep_return=L.ptr(self.ep_return), frames=L.ptr(self.frames))
+                             ep_return=L.ptr(self.ep_return), frames=L.ptr(self.frames), last_h1=L.ptr(self.last_h1),
+                             last_h2=L.ptr(self.last_h2))
 
     def _obs_buf(self):
         return torch.empty((self.state_dim, self.n), dtype=self.dtype, device=self.device)
@@ -295,18 +302,23 @@ class PHVec(_VecBase):
 
     MODE = {"none": L.PH_NO_INTEGRATOR, "integrator": L.PH_INTEGRATOR, "nobound": L.PH_INTEGRATOR_NOBOUND}
 
-    def __init__(self, n: int, dtype=torch.float32, device="cuda", integrator="integrator", seed=0, env_offset=0, **cfg):
+    def __init__(self, n: int, dtype=torch.float32, device="cuda", integrator="integrator", seed=0, env_offset=0,
+                 reset_from_last_state=False, **cfg):
         self.device = _require_cuda(device)
         self.n, self.dtype, self.seed, self.env_offset = int(n), dtype, int(seed), int(env_offset)
-        self.cfg = L.ph_config(integrator_mode=self.MODE[integrator], **cfg)
+        self.cfg = L.ph_config(integrator_mode=self.MODE[integrator], reset_from_last_state=int(bool(reset_from_last_state)),
+                               **cfg)
         self.state_dim = 2 if integrator == "none" else 3
         self.integrator = integrator
         self._alloc(["x", "y", "r", "I", "A", "B", "C", "qww_V", "qc_V"], self.n)
         t64, t32 = ph_table(self.cfg, self.device)
         self.table = t64 if dtype == torch.float64 else t32
+        # state at the last time-limit step (ph.py:102, :345-346); NaN = None
+        self.last_x = (torch.full((self.n,), float("nan"), dtype=dtype, device=self.device) if reset_from_last_state else None)
         self._st = L.PhState(x=L.ptr(self.x), y=L.ptr(self.y), r=L.ptr(self.r), I=L.ptr(self.I), A=L.ptr(self.A),
                              B=L.ptr(self.B), C=L.ptr(self.C), qww_V=L.ptr(self.qww_V), qc_V=L.ptr(self.qc_V),
-                             t=L.ptr(self.t), episode=L.ptr(self.episode), ep_return=L.ptr(self.ep_return))
+                             t=L.ptr(self.t), episode=L.ptr(self.episode), ep_return=L.ptr(self.ep_return),
+                             last_x=L.ptr(self.last_x))
 
     def _obs_buf(self):
         return torch.empty((self.state_dim, self.n), dtype=self.dtype, device=self.device)

@@ -109,7 +109,7 @@ def test_reference_error_behaviour(G):
     with pytest.raises(IndexError):           # table overflow (ph.py:188)
         ph.set_state(1e9)
     with pytest.raises(NotImplementedError):
-        G.make(WT_INT, reset_from_last_state=True)
+        G.make(WT_INT, controller_type="LQR")
 
 
 def test_deepcopy_gives_an_independent_env(G):
@@ -175,3 +175,84 @@ def test_full_size_properties_at_2_pow_20_envs():
     assert torch.equal(torch.cat([lo.h2, hi.h2]), whole.h2) and torch.equal(torch.cat([lo.ep_return, hi.ep_return]), whole.ep_return)
     mean_ret = st[0] / st[2]
     assert -4000 < mean_ret < -500                                          # the P prior on random set-points (SquareDistance)
+
+
+def test_reset_from_last_state_follows_the_reference_script(G, golden):
+    """reset_from_last_state=True (nonlinear_watertank.py:904-910, :819-821; ph.py:417-420, :345-346) against the
+    scripted run of the reference in tests/golden/last_state.npz (oracle/gen_golden.py:gen_last_state): the ensemble
+    member and set-point drawn by each reset are replayed through the public setters, the levels are the kernels'."""
+    d = golden("last_state")
+    env = G.make(WT_INT, reset_from_last_state=True, max_step=6, noise_scale=0.0, reward_type="distance")
+    assert env.last_h1 is None and env.last_h2 is None
+    first = True
+    for (kind, arg), row in zip(d["wt_script"], d["wt_rows"]):
+        h1, h2, r, I, t, l1, l2, a1, a2, Kp = row
+        if kind == 0:
+            env.reset()
+            if first:                                   # no finished episode yet: |N(0,1)| * 0.1 (:905-907)
+                assert 0.0 <= env.h1 < 1.0 and 0.0 <= env.h2 < 1.0 and env.last_h1 is None
+                env.set_state(h1, h2)
+                first = False
+            env.reset_changable_parameters(a1, a2, Kp)
+            env.set_r(r)
+        else:
+            _, _, done, _ = env.step(np.array([arg]))
+            assert done == (t == 6)
+        assert (env.h1, env.h2, env.integrator, env._episode_steps) == (h1, h2, I, int(t))
+        assert (env.last_h1, env.last_h2) == ((None, None) if np.isnan(l1) else (l1, l2))
+
+    ph = G.make(PH_INT, reset_from_last_state=True)
+    assert ph.last_state is None
+    for (kind, arg), row in zip(d["ph_script"], d["ph_rows"]):
+        x, y, r, I, t, last, qww, qc, done_ref = row
+        if kind == 0:
+            ph.reset()
+            if np.isnan(last):
+                assert 0.0 <= ph.state < 50.0          # ph.py:420
+                ph.set_state(x)
+            else:
+                assert ph.state == ph.last_state        # kept across the reset, whatever the new ensemble member is
+                np.testing.assert_allclose(ph.state, last, rtol=1e-10)   # (B differs from scipy's c2d in the 16th digit)
+            ph.set_params(qww, qc)
+            ph.update_system()
+            ph.set_state(ph.state)                      # y = observe_state(x) with the replayed C (:422)
+            ph.set_r(r)
+        else:
+            _, _, done, _ = ph.step(np.array([arg]))
+            assert done == bool(done_ref)
+        np.testing.assert_allclose([ph.state, ph.y, ph.integrator], [x, y, I], rtol=1e-10, atol=1e-10)
+        assert ph._episode_steps == int(t)
+        if np.isnan(last):
+            assert ph.last_state is None
+        else:
+            np.testing.assert_allclose(ph.last_state, last, rtol=1e-10)
+
+
+def test_reset_from_last_state_in_the_fused_rollout(oracle):
+    """The in-kernel auto-reset keeps the levels (every in-kernel reset follows a done) and records them; the first
+    reset of a fresh env draws |N(0,1)| * 0.1 from the Box-Muller pair of the (h1, h2) uniforms."""
+    import pime_b200.vec as V
+    n, T = 4096, 7
+    K = np.array([0.0, 0.4, -0.4, 0.0])
+    env = V.WaterTankVec(n, dtype=torch.float64, seed=3, reset_from_last_state=True, max_step=T, noise_scale=0.0)
+    env.reset()
+    u = np.stack([oracle.reset_uniforms(3, i, 0) for i in range(64)])
+    rad = np.sqrt(-2.0 * np.log1p(-u[:, 3]))
+    np.testing.assert_allclose(env.h1[:64].cpu().numpy(), np.abs(rad * np.cos(2 * np.pi * u[:, 4])) * 0.1, rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(env.h2[:64].cpu().numpy(), np.abs(rad * np.sin(2 * np.pi * u[:, 4])) * 0.1, rtol=1e-12, atol=1e-15)
+    assert torch.isnan(env.last_h1).all()
+    twin = V.WaterTankVec(n, dtype=torch.float64, seed=3, reset_from_last_state=True, max_step=T, noise_scale=0.0)
+    twin.reset()
+    env.rollout(T, -K, deterministic=True, auto_reset=True)            # ends exactly on the done step, then resets
+    twin.rollout(T, -K, deterministic=True, auto_reset=False)
+    assert torch.equal(env.h1, twin.h1) and torch.equal(env.h2, twin.h2)            # levels survive the reset ...
+    assert torch.equal(env.last_h1, twin.h1) and torch.equal(env.last_h2, twin.h2)  # ... and are what `done` recorded
+    assert int(env.t.max()) == 0 and int(twin.t.min()) == T and not torch.equal(env.r, twin.r)
+    ph = V.PHVec(n, dtype=torch.float64, seed=5, reset_from_last_state=True, max_episode_steps=T)
+    ph.reset()
+    ph2 = V.PHVec(n, dtype=torch.float64, seed=5, reset_from_last_state=True, max_episode_steps=T)
+    ph2.reset()
+    Kp = np.array([-0.02, 0.02, 0.035])
+    ph.rollout(T, -Kp, deterministic=True, auto_reset=True)
+    ph2.rollout(T, -Kp, deterministic=True, auto_reset=False)
+    assert torch.equal(ph.x, ph2.x) and torch.equal(ph.last_x, ph2.x) and not torch.equal(ph.C, ph2.C)
