@@ -19,6 +19,9 @@ struct RolloutParams {
     uint32_t tick0;
     int S;
     double priorK[kMaxS];
+    float priorKf[kMaxS];   // float(priorK): the f32 path multiplies in fp32, as obs32 @ priorK does (agent_residual.py:61)
+    float reward_scale_f, gamma_f;
+    int reward_scale_exact;  // reward_scale is a float: float(double(rew) * reward_scale) == rew * float(reward_scale)
     const float *eps;
     const void *pn1, *pn2;
     float *buf_state, *buf_other;
@@ -35,6 +38,7 @@ constexpr int kMaxFrames = 30;
 
 template <typename T, bool STACK> struct WtGlue {
     using Real = T;
+    static constexpr int kObsMax = STACK ? kMaxFrames : 4;   // widest observation of this plant (loop bounds)
     WtConst<T> c;
     T *h1, *h2, *r, *I, *a1, *a2, *Kp, *ep_return, *frames, *last_h1, *last_h2;
     int32_t *t;
@@ -123,6 +127,7 @@ template <typename T, bool STACK> struct WtGlue {
 
 template <typename T> struct PhGlue {
     using Real = T;
+    static constexpr int kObsMax = 3;
     PhConst<T> c;
     const T *table;
     T *x, *y, *r, *I, *A, *B, *C, *qww, *qc, *ep_return, *last_x;
@@ -174,6 +179,10 @@ template <typename T> struct PhGlue {
     }
 };
 
+template <typename T> __device__ __forceinline__ T prior_k(const RolloutParams &rp, int k);
+template <> __device__ __forceinline__ float prior_k<float>(const RolloutParams &rp, int k) { return rp.priorKf[k]; }
+template <> __device__ __forceinline__ double prior_k<double>(const RolloutParams &rp, int k) { return rp.priorK[k]; }
+
 // ------------------------------------------------------------------------------------------------ one env step
 // Everything of one step that follows the actor forward, for the env owned by the calling thread:
 // noise, action = tanh(a_raw) + obs32 . priorK, plant step, replay row, statistics, auto-reset.
@@ -209,15 +218,15 @@ template <typename Plant> struct Stepper {
         if (rp.deterministic) {
             float prior = 0.0f;
 #pragma unroll
-            for (int k = 0; k < kMaxS; ++k)
-                if (k < S) prior = fmaf(obs[k], (float)rp.priorK[k], prior);
+            for (int k = 0; k < Plant::kObsMax; ++k)
+                if (k < S) prior = fmaf(obs[k], rp.priorKf[k], prior);
             a_raw = a_avg;
             action = (T)(tanhf(a_avg) + prior);
         } else {
             T prior = (T)0;
 #pragma unroll
-            for (int k = 0; k < kMaxS; ++k)
-                if (k < S) prior = N::add(prior, N::mul((T)obs[k], (T)rp.priorK[k]));
+            for (int k = 0; k < Plant::kObsMax; ++k)
+                if (k < S) prior = N::add(prior, N::mul((T)obs[k], prior_k<T>(rp, k)));
             a_raw = a_avg + eps * rp.a_std;   // net_residual.py:176-180
             action = N::add((T)tanhf(a_raw), prior);
         }
@@ -233,15 +242,16 @@ template <typename Plant> struct Stepper {
                     *reinterpret_cast<float4 *>(bs) = make_float4(obs[0], obs[1], obs[2], obs[3]);
                 } else if ((S & 1) == 0) {   // rows of an even number of floats are 8-byte aligned
 #pragma unroll
-                    for (int k = 0; k < kMaxS; k += 2)
+                    for (int k = 0; k + 1 < Plant::kObsMax; k += 2)
                         if (k < S) *reinterpret_cast<float2 *>(bs + k) = make_float2(obs[k], obs[k + 1]);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < kMaxS; ++k)
+                    for (int k = 0; k < Plant::kObsMax; ++k)
                         if (k < S) bs[k] = obs[k];
                 }
-                *reinterpret_cast<float4 *>(rp.buf_other + q * 4) =
-                    make_float4((float)((double)rew * rp.reward_scale), done ? 0.0f : (float)rp.gamma, a_raw, eps);
+                const float rs = (sizeof(T) == 4 && rp.reward_scale_exact) ? (float)rew * rp.reward_scale_f
+                                                                           : (float)((double)rew * rp.reward_scale);
+                *reinterpret_cast<float4 *>(rp.buf_other + q * 4) = make_float4(rs, done ? 0.0f : rp.gamma_f, a_raw, eps);
             }
             if (rp.env_action) ((T *)rp.env_action)[q] = action;
             s_rew += (double)rew;
@@ -307,21 +317,34 @@ __global__ void __launch_bounds__(tc::kThreads, 1) rollout_kernel(Plant plant, t
         eng.write_obs(row, 0, obs);
         plant.observe(env1, obs);
         eng.write_obs(row, 1, obs);
+#ifdef PIME_PROFILE_OWNER
+        long long c_wait = 0, c_work = 0, c0 = clock64();
+#define PIME_TICK(acc) { const long long c1 = clock64(); acc += c1 - c0; c0 = c1; }
+#else
+#define PIME_TICK(acc)
+#endif
         for (int s = 0; s < rp.T; ++s) {
             const bool more = s + 1 < rp.T;
             {   // group 0: its network pass is 2s; the workers run group 1's pass while this thread steps the plant
                 const float a_avg = eng.read_out(row, 2 * s);
+                PIME_TICK(c_wait)
                 plant.observe(env0, obs);
                 sp.step(plant, rp, env0, obs, a_avg, s, ii0, live0);
                 if (more) { plant.observe(env0, obs); eng.write_obs(row, 0, obs); }
+                PIME_TICK(c_work)
             }
             {
                 const float a_avg = eng.read_out(row, 2 * s + 1);
+                PIME_TICK(c_wait)
                 plant.observe(env1, obs);
                 sp.step(plant, rp, env1, obs, a_avg, s, ii1, live1);
                 if (more) { plant.observe(env1, obs); eng.write_obs(row, 1, obs); }
+                PIME_TICK(c_work)
             }
         }
+#ifdef PIME_PROFILE_OWNER
+        if (blockIdx.x == 0 && row == 0 && rp.stats) { rp.stats[6] = (double)c_wait; rp.stats[7] = (double)c_work; }
+#endif
         if (live0) plant.store(env0, i0, n);
         if (live1) plant.store(env1, i1, n);
         fault = sp.fault;
@@ -410,7 +433,13 @@ inline int fill_rollout_params(const pime_rollout_args *a, int64_t n, int S, Rol
     rp.a_std = expf(a->a_std_log);
     rp.reward_scale = a->reward_scale; rp.gamma = a->gamma; rp.seed = a->seed; rp.env_offset = a->env_offset; rp.tick0 = a->tick0;
     rp.S = S;
-    for (int k = 0; k < kMaxS; ++k) rp.priorK[k] = k < S ? a->priorK_host[k] : 0.0;
+    for (int k = 0; k < kMaxS; ++k) {
+        rp.priorK[k] = k < S ? a->priorK_host[k] : 0.0;
+        rp.priorKf[k] = (float)rp.priorK[k];
+    }
+    rp.reward_scale_f = (float)a->reward_scale;
+    rp.reward_scale_exact = (double)rp.reward_scale_f == a->reward_scale;
+    rp.gamma_f = (float)a->gamma;
     rp.eps = a->eps; rp.pn1 = a->pnoise1; rp.pn2 = a->pnoise2;
     rp.buf_state = a->buf_state; rp.buf_other = a->buf_other; rp.env_action = a->env_action;
     rp.stats = a->stats; rp.status = a->status;
