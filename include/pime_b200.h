@@ -279,6 +279,46 @@ int pime_reduce_episode_stats_f64(int64_t n, const double *ep_return, double *st
 int pime_wt_rollout_host_f32(const pime_wt_config *cfg, int64_t n, const pime_wt_state *st_host, const pime_wt_state *st_dev,
                              const pime_rollout_args *args, float *ep_return_host, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * PPO learner: one minibatch step of AgentPPO.update_net (elegantrl/agent.py:635-658) on the GPU-resident replay
+ * in two launches (rows kernel: gather + actor / critic forward + objectives + data gradients; weight-gradient
+ * kernel with the Adam update fused in).  fp32 throughout, torch.optim.Adam arithmetic.
+ *
+ *   new_logprob = compute_logprob(state, action)                       net_residual.py:62-66
+ *   ratio       = exp(new_logprob - logprob)
+ *   obj_actor   = -mean(min(adv*ratio, adv*clamp(ratio, 1-clip, 1+clip))) + lambda_entropy * mean(exp(lp)*lp)
+ *   obj_critic  = SmoothL1(critic(state), r_sum)
+ *   obj_united  = obj_actor + obj_critic / (r_sum.std() + 1e-5);  Adam step on actor, critic and a_std_log
+ *
+ * theta = [actor parameters | critic parameters | a_std_log], each net in state_dict order (pime_actor_param_count
+ * floats; the critic is CriticAdv with the actor's S and H); theta_t holds every weight matrix transposed
+ * (pime_ppo_transpose; kept up to date by the step).  state: device int32[4], zero-initialised, owned by the
+ * library between steps (Adam step count, a ticket, the a_std_log gradient accumulator).  loss_ring: device
+ * float[ring_len][4], zero-initialised; step t (0-based count before the call) adds the means of (obj_united,
+ * obj_actor, obj_critic, obj_entropy) to row t % ring_len and clears the next row.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct pime_ppo_args {
+    const pime_actor_config *actor;   /* PIME_ACTOR_PLAIN or PIME_ACTOR_MODULAR                               */
+    float *theta, *theta_t;           /* [pime_ppo_theta_count]                                                */
+    float *adam_m, *adam_v;           /* Adam moments, same layout; may be NULL when grad_out is given         */
+    float *grad_out;                  /* not NULL: write the gradient of obj_united here and leave theta alone */
+    const float *buf_state;           /* [buf_len][S]                                                          */
+    const float *buf_action, *buf_r_sum, *buf_logprob, *buf_advantage; /* [buf_len]                            */
+    const int64_t *idx;               /* [batch] rows of this minibatch (torch.randint, agent.py:636)          */
+    int32_t batch;
+    float ratio_clip, lambda_entropy;
+    float lr, beta1, beta2, eps;      /* torch.optim.Adam                                                      */
+    int32_t *state;
+    float *work;                      /* scratch: pime_ppo_work_floats(actor, batch) floats                    */
+    float *loss_ring;
+    int32_t ring_len;
+} pime_ppo_args;
+
+int64_t pime_ppo_theta_count(const pime_actor_config *actor);
+int64_t pime_ppo_work_floats(const pime_actor_config *actor, int32_t batch);
+int pime_ppo_transpose(const pime_actor_config *actor, const float *theta, float *theta_t, void *stream);
+int pime_ppo_step(const pime_ppo_args *args, void *stream);
+
 /* misc */
 int pime_abi_version(void);
 const char *pime_last_error(void);

@@ -64,6 +64,14 @@ class RolloutArgs(C.Structure):
                 ("buf_state", vp), ("buf_other", vp), ("env_action", vp), ("stats", vp), ("status", vp)]
 
 
+class PpoArgs(C.Structure):
+    _fields_ = [("actor", C.POINTER(ActorConfig)), ("theta", vp), ("theta_t", vp), ("adam_m", vp), ("adam_v", vp),
+                ("grad_out", vp), ("buf_state", vp), ("buf_action", vp), ("buf_r_sum", vp), ("buf_logprob", vp),
+                ("buf_advantage", vp), ("idx", vp), ("batch", C.c_int32), ("ratio_clip", C.c_float),
+                ("lambda_entropy", C.c_float), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("state", vp), ("work", vp), ("loss_ring", vp), ("ring_len", C.c_int32)]
+
+
 # every symbol include/pime_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
     "pime_wt_default_config", "pime_wt_reset_f32", "pime_wt_reset_f64", "pime_wt_step_f32", "pime_wt_step_f64",
@@ -73,6 +81,7 @@ SYMBOLS = [
     "pime_actor_param_count", "pime_actor_pack_bytes", "pime_actor_block_list", "pime_actor_pack", "pime_actor_forward",
     "pime_wt_rollout_f32", "pime_wt_rollout_f64", "pime_ph_rollout_f32", "pime_ph_rollout_f64",
     "pime_gae_scan", "pime_reduce_episode_stats_f32", "pime_reduce_episode_stats_f64",
+    "pime_ppo_theta_count", "pime_ppo_work_floats", "pime_ppo_transpose", "pime_ppo_step",
     "pime_wt_rollout_host_f32", "pime_abi_version", "pime_last_error", "pime_device_info", "pime_philox_probe",
 ]
 
@@ -94,6 +103,8 @@ def lib() -> C.CDLL:
         L.pime_last_error.restype = C.c_char_p
         L.pime_actor_param_count.restype = C.c_int64
         L.pime_actor_pack_bytes.restype = C.c_int64
+        L.pime_ppo_theta_count.restype = C.c_int64
+        L.pime_ppo_work_floats.restype = C.c_int64
         for name in SYMBOLS:
             getattr(L, name)
         _lib = L

@@ -1,0 +1,577 @@
+// learner.cu -- one PPO minibatch step of AgentPPO.update_net (elegantrl/agent.py:635-658) on the GPU-resident replay
+// as TWO launches instead of the ~100 small kernels of the autograd step (the reference's batch sizes, 128-512 rows, are
+// launch-latency bound):
+//
+//   ppo_rows_kernel   one CTA per R minibatch rows: gather the rows, actor and critic forward (fp32, activations in
+//                     shared memory), the clipped-surrogate / entropy / SmoothL1 objectives and their gradients, the
+//                     data-gradient chain through both networks.  Rows are independent, so no grid-wide step exists;
+//                     weights stream from L2 (forward from the transposed copy, backward from the torch layout, so that
+//                     both are coalesced).  Activations and pre-activation gradients go to a scratch buffer.
+//   ppo_wgrad_kernel  one CTA per 64 x 64 tile of a weight matrix: dW = dZ^T . A over the minibatch, bias gradient, and
+//                     the Adam update (torch.optim.Adam arithmetic) applied in place to the weights, their transposed
+//                     copy and the moments.  Every gradient element is produced by exactly one thread: no atomics.
+//
+// fp32 throughout (the reference trains in fp32); sums run in a different order than cuBLAS, nothing else differs.
+#include "pime_common.cuh"
+#include "tc_mlp.cuh"
+
+namespace pime {
+namespace ppo {
+
+constexpr int kThreads = 256;
+constexpr int kMaxLayers = 10;
+constexpr int kXStride = 32;      // gathered state row (S <= 32)
+constexpr int kRowVals = 8;       // per-row scalars in shared memory
+constexpr int kTile = 64;         // weight-gradient tile
+constexpr int kBk = 32;           // minibatch rows per shared-memory stage of the weight-gradient kernel
+
+enum { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2 };
+
+struct LayerDesc {
+    int net;              // 0 actor, 1 critic
+    int N, K;
+    int w_off, b_off;     // offsets into theta
+    int dz_col;           // column of this layer's dZ in the net's gradient rows; -1: the output gradient DOUT[:, net]
+    int in_col;           // column of the layer's input in the net's activation rows; -1: the gathered state X[:, x_col:]
+    int x_col;
+    int tile0, tn, tk;    // first tile, tiles along N and K
+};
+
+struct NetDims {
+    int kind, S, H, So, LA;   // LA: activation columns per row
+    int theta_off;            // first parameter of this net in theta
+    int src[12];              // offsets of the state_dict tensors inside the net's parameters
+};
+
+struct StepParams {
+    NetDims act, cri;
+    int n_layers, n_tiles;
+    LayerDesc layer[kMaxLayers];
+    float *theta, *theta_t, *m, *v, *grad_out;
+    int n_theta;              // actor + critic + a_std_log
+    const float *buf_state, *buf_action, *buf_r_sum, *buf_logprob, *buf_adv;
+    const int64_t *idx;
+    int B;
+    float ratio_clip, lambda_entropy, lr, beta1, beta2, eps;
+    int *step_dev;            // Adam step count so far (the step being taken is *step_dev + 1)
+    unsigned *ticket;
+    float *g_astd;            // accumulated gradient of a_std_log
+    float *X, *ACT_A, *DZ_A, *ACT_C, *DZ_C, *DOUT;
+    float *loss_ring;
+    int ring_len;
+};
+
+__device__ __forceinline__ float act_apply(int act, float x) { return act == ACT_TANH ? tanhf(x) : (act == ACT_RELU ? fmaxf(x, 0.0f) : x); }
+__device__ __forceinline__ float act_grad(int act, float a) { return act == ACT_TANH ? 1.0f - a * a : (act == ACT_RELU ? (a > 0.0f ? 1.0f : 0.0f) : 1.0f); }
+
+// out[r][n] = act(b[n] + sum_k in[r][k] Wt[k][n]); thread n, R rows in registers, weights coalesced along n
+template <int R>
+__device__ __forceinline__ void fwd_layer(const float *in, int in_stride, int K, const float *__restrict__ Wt,
+                                          const float *__restrict__ bias, int N, int act, float *out, int out_stride) {
+    for (int n = threadIdx.x; n < N; n += kThreads) {
+        float acc[R];
+        const float b = __ldg(bias + n);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = b;
+        int k = 0;
+        for (; k + 8 <= K; k += 8) {
+            float w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = __ldg(Wt + (size_t)(k + j) * N + n);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 a0 = *reinterpret_cast<const float4 *>(in + r * in_stride + k);
+                const float4 a1 = *reinterpret_cast<const float4 *>(in + r * in_stride + k + 4);
+                acc[r] = fmaf(a0.x, w[0], acc[r]); acc[r] = fmaf(a0.y, w[1], acc[r]);
+                acc[r] = fmaf(a0.z, w[2], acc[r]); acc[r] = fmaf(a0.w, w[3], acc[r]);
+                acc[r] = fmaf(a1.x, w[4], acc[r]); acc[r] = fmaf(a1.y, w[5], acc[r]);
+                acc[r] = fmaf(a1.z, w[6], acc[r]); acc[r] = fmaf(a1.w, w[7], acc[r]);
+            }
+        }
+        for (; k < K; ++k) {
+            const float w = __ldg(Wt + (size_t)k * N + n);
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = fmaf(in[r * in_stride + k], w, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[r * out_stride + n] = act_apply(act, acc[r]);
+    }
+}
+
+// Linear(K -> 1): one warp per row
+template <int R>
+__device__ __forceinline__ void fwd_out(const float *in, int in_stride, int K, const float *__restrict__ w, float b, float *out,
+                                        int out_stride) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < R; r += kThreads / 32) {
+        float s = 0.0f;
+        for (int k = lane; k < K; k += 32) s = fmaf(in[r * in_stride + k], __ldg(w + k), s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) out[r * out_stride] = s + b;
+    }
+}
+
+// dz_in[r][k] = act'(a_in[r][k]) * sum_n dz_out[r][n] W[n][k]; thread k, weights coalesced along k
+template <int R>
+__device__ __forceinline__ void bwd_layer(const float *dz_out, int dzo_stride, int N, const float *__restrict__ W, int K,
+                                          const float *a_in, int a_stride, int act_in, float *dz_in, int dzi_stride) {
+    for (int k = threadIdx.x; k < K; k += kThreads) {
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.0f;
+        for (int n = 0; n + 8 <= N; n += 8) {
+            float w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = __ldg(W + (size_t)(n + j) * K + k);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 d0 = *reinterpret_cast<const float4 *>(dz_out + r * dzo_stride + n);
+                const float4 d1 = *reinterpret_cast<const float4 *>(dz_out + r * dzo_stride + n + 4);
+                acc[r] = fmaf(d0.x, w[0], acc[r]); acc[r] = fmaf(d0.y, w[1], acc[r]);
+                acc[r] = fmaf(d0.z, w[2], acc[r]); acc[r] = fmaf(d0.w, w[3], acc[r]);
+                acc[r] = fmaf(d1.x, w[4], acc[r]); acc[r] = fmaf(d1.y, w[5], acc[r]);
+                acc[r] = fmaf(d1.z, w[6], acc[r]); acc[r] = fmaf(d1.w, w[7], acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) dz_in[r * dzi_stride + k] = acc[r] * act_grad(act_in, a_in[r * a_stride + k]);
+    }
+}
+
+// backward of Linear(K -> 1): dz_in[r][k] = act'(a_in[r][k]) * d_out[r] * w[k]
+template <int R>
+__device__ __forceinline__ void bwd_out(const float *d_out, int d_stride, const float *__restrict__ w, int K, const float *a_in,
+                                        int a_stride, int act_in, float *dz_in, int dzi_stride) {
+    for (int k = threadIdx.x; k < K; k += kThreads) {
+        const float wk = __ldg(w + k);
+#pragma unroll
+        for (int r = 0; r < R; ++r) dz_in[r * dzi_stride + k] = d_out[r * d_stride] * wk * act_grad(act_in, a_in[r * a_stride + k]);
+    }
+}
+
+__device__ __forceinline__ float block_sum(float v, float *scratch) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s += scratch[w];
+    return s;
+}
+
+// forward (and its mirror, the data-gradient chain) of one net on R rows held in shared memory
+template <int R>
+__device__ __forceinline__ void net_forward(const NetDims &d, const float *__restrict__ th, const float *__restrict__ tt, const float *sX,
+                                            float *A, int as, float *out, int out_stride) {
+    const int H = d.H;
+    if (d.kind == PIME_ACTOR_MODULAR) {   // net_residual.py:150-170
+        const int Hh = H / 2;
+        fwd_layer<R>(sX, kXStride, d.So, tt + d.src[0], th + d.src[1], H, ACT_TANH, A, as);                       // other_net.0
+        fwd_layer<R>(sX + d.So, kXStride, d.S - d.So, tt + d.src[4], th + d.src[5], H, ACT_TANH, A + H, as);     // integrator_net.0
+        __syncthreads();
+        fwd_layer<R>(A, as, H, tt + d.src[2], th + d.src[3], Hh, ACT_TANH, A + 2 * H, as);                        // other_net.2
+        fwd_layer<R>(A + H, as, H, tt + d.src[6], th + d.src[7], Hh, ACT_TANH, A + 2 * H + Hh, as);               // integrator_net.2
+        __syncthreads();
+        fwd_layer<R>(A + 2 * H, as, H, tt + d.src[8], th + d.src[9], H, ACT_TANH, A + 3 * H, as);                 // net.0 on cat
+        __syncthreads();
+        fwd_out<R>(A + 3 * H, as, H, th + d.src[10], __ldg(th + d.src[11]), out, out_stride);                     // net.2
+    } else {                               // plain actor (tanh) / CriticAdv (relu)
+        const int act = d.kind == PIME_CRITIC_ADV ? ACT_RELU : ACT_TANH;
+        fwd_layer<R>(sX, kXStride, d.S, tt + d.src[0], th + d.src[1], H, act, A, as);
+        __syncthreads();
+        fwd_layer<R>(A, as, H, tt + d.src[2], th + d.src[3], H, act, A + H, as);
+        __syncthreads();
+        fwd_layer<R>(A + H, as, H, tt + d.src[4], th + d.src[5], H, act, A + 2 * H, as);
+        __syncthreads();
+        fwd_out<R>(A + 2 * H, as, H, th + d.src[6], __ldg(th + d.src[7]), out, out_stride);
+    }
+    __syncthreads();
+}
+
+template <int R>
+__device__ __forceinline__ void net_backward(const NetDims &d, const float *__restrict__ th, const float *A, float *Z, int as,
+                                             const float *d_out, int d_stride) {
+    const int H = d.H;
+    if (d.kind == PIME_ACTOR_MODULAR) {
+        const int Hh = H / 2;
+        bwd_out<R>(d_out, d_stride, th + d.src[10], H, A + 3 * H, as, ACT_TANH, Z + 3 * H, as);                   // -> dZ(net.0)
+        __syncthreads();
+        bwd_layer<R>(Z + 3 * H, as, H, th + d.src[8], H, A + 2 * H, as, ACT_TANH, Z + 2 * H, as);                 // -> dZ(other_net.2 | integrator_net.2)
+        __syncthreads();
+        bwd_layer<R>(Z + 2 * H, as, Hh, th + d.src[2], H, A, as, ACT_TANH, Z, as);                                // -> dZ(other_net.0)
+        bwd_layer<R>(Z + 2 * H + Hh, as, Hh, th + d.src[6], H, A + H, as, ACT_TANH, Z + H, as);                   // -> dZ(integrator_net.0)
+    } else {
+        const int act = d.kind == PIME_CRITIC_ADV ? ACT_RELU : ACT_TANH;
+        bwd_out<R>(d_out, d_stride, th + d.src[6], H, A + 2 * H, as, act, Z + 2 * H, as);
+        __syncthreads();
+        bwd_layer<R>(Z + 2 * H, as, H, th + d.src[4], H, A + H, as, act, Z + H, as);
+        __syncthreads();
+        bwd_layer<R>(Z + H, as, H, th + d.src[2], H, A, as, act, Z, as);
+    }
+    __syncthreads();
+}
+
+template <int R>
+__global__ void __launch_bounds__(kThreads) ppo_rows_kernel(const StepParams p) {
+    extern __shared__ __align__(16) float sm[];
+    const int LAa = p.act.LA, LAc = p.cri.LA, LA = LAa + LAc;
+    float *sX = sm;                         // [R][kXStride]
+    float *sA = sX + R * kXStride;          // [R][LA] activations: actor | critic
+    float *sZ = sA + R * LA;                // [R][LA] pre-activation gradients
+    float *sV = sZ + R * LA;                // [R][kRowVals]: action, r_sum, logprob_old, advantage, a_avg, value, d_a, d_v
+    float *sRed = sV + R * kRowVals;        // [8]
+    const int tid = threadIdx.x;
+    const int B = p.B;
+    const int b0 = blockIdx.x * R;
+
+    // r_sum.std() of the minibatch (agent.py:652; unbiased), two passes
+    float s = 0.0f;
+    for (int i = tid; i < B; i += kThreads) s += __ldg(p.buf_r_sum + __ldg(p.idx + i));
+    const float mean = block_sum(s, sRed) / (float)B;
+    s = 0.0f;
+    for (int i = tid; i < B; i += kThreads) {
+        const float dlt = __ldg(p.buf_r_sum + __ldg(p.idx + i)) - mean;
+        s = fmaf(dlt, dlt, s);
+    }
+    const float rstd = sqrtf(block_sum(s, sRed) / (float)(B > 1 ? B - 1 : 1));
+    const float inv_cs = 1.0f / (rstd + 1e-5f);
+
+    // gather
+    for (int j = tid; j < R * kXStride; j += kThreads) {
+        const int r = j / kXStride, c = j % kXStride, b = b0 + r;
+        float x = 0.0f;
+        if (b < B && c < p.act.S) x = __ldg(p.buf_state + __ldg(p.idx + b) * p.act.S + c);
+        sX[j] = x;
+    }
+    if (tid < R) {
+        const int b = b0 + tid;
+        const bool live = b < B;
+        const int64_t i = live ? __ldg(p.idx + b) : 0;
+        sV[tid * kRowVals + 0] = live ? __ldg(p.buf_action + i) : 0.0f;
+        sV[tid * kRowVals + 1] = live ? __ldg(p.buf_r_sum + i) : 0.0f;
+        sV[tid * kRowVals + 2] = live ? __ldg(p.buf_logprob + i) : 0.0f;
+        sV[tid * kRowVals + 3] = live ? __ldg(p.buf_adv + i) : 0.0f;
+    }
+    __syncthreads();
+
+    const float *thA = p.theta + p.act.theta_off, *ttA = p.theta_t + p.act.theta_off;
+    const float *thC = p.theta + p.cri.theta_off, *ttC = p.theta_t + p.cri.theta_off;
+    net_forward<R>(p.act, thA, ttA, sX, sA, LA, sV + 4, kRowVals);
+    net_forward<R>(p.cri, thC, ttC, sX, sA + LAa, LA, sV + 5, kRowVals);
+
+    // objectives and their gradients (agent.py:635-652), one thread per row
+    if (tid < R) {
+        float *rv = sV + tid * kRowVals;
+        const bool live = b0 + tid < B;
+        const float invB = 1.0f / (float)B;
+        const float asl = __ldg(p.theta + p.n_theta - 1);
+        const float std = expf(asl);
+        const float dd = (rv[4] - rv[0]) / std;
+        const float lp = -(asl + 0.9189385332046727f + dd * dd * 0.5f);      // compute_logprob (net_residual.py:62-66)
+        const float ratio = expf(lp - rv[2]);
+        const float adv = rv[3];
+        const float s1 = adv * ratio;
+        const float s2 = adv * fminf(fmaxf(ratio, 1.0f - p.ratio_clip), 1.0f + p.ratio_clip);
+        const float sur = fminf(s1, s2);
+        const float elp = expf(lp);
+        const float ent = elp * lp;
+        const float g_lp = (-(s1 <= s2 ? s1 : 0.0f) + p.lambda_entropy * (ent + elp)) * invB;   // d united / d new_logprob
+        const float e = rv[5] - rv[1];
+        const float ae = fabsf(e);
+        const float l1 = ae < 1.0f ? 0.5f * e * e : ae - 0.5f;                   // SmoothL1Loss, beta = 1
+        rv[6] = live ? g_lp * (-dd / std) : 0.0f;                                // d united / d a_avg
+        rv[7] = live ? fminf(fmaxf(e, -1.0f), 1.0f) * invB * inv_cs : 0.0f;      // d united / d value
+        float o_act = live ? (-sur + p.lambda_entropy * ent) * invB : 0.0f;
+        float o_cri = live ? l1 * invB : 0.0f;
+        float o_ent = live ? ent * invB : 0.0f;
+        float g_asl = live ? g_lp * (dd * dd - 1.0f) : 0.0f;
+#pragma unroll
+        for (int o = 1; o < R; o <<= 1) {   // R is a power of two <= 32, the rows sit in one warp
+            o_act += __shfl_xor_sync((1u << R) - 1u, o_act, o);
+            o_cri += __shfl_xor_sync((1u << R) - 1u, o_cri, o);
+            o_ent += __shfl_xor_sync((1u << R) - 1u, o_ent, o);
+            g_asl += __shfl_xor_sync((1u << R) - 1u, g_asl, o);
+        }
+        if (tid == 0) {
+            float *row = p.loss_ring + (size_t)(*p.step_dev % p.ring_len) * 4;
+            atomicAdd(row + 0, o_act + o_cri * inv_cs);
+            atomicAdd(row + 1, o_act);
+            atomicAdd(row + 2, o_cri);
+            atomicAdd(row + 3, o_ent);
+            atomicAdd(p.g_astd, g_asl);
+        }
+    }
+    __syncthreads();
+
+    net_backward<R>(p.act, thA, sA, sZ, LA, sV + 6, kRowVals);
+    net_backward<R>(p.cri, thC, sA + LAa, sZ + LAa, LA, sV + 7, kRowVals);
+
+    // rows -> scratch (inputs of the weight-gradient kernel)
+    for (int r = 0; r < R; ++r) {
+        const int b = b0 + r;
+        if (b >= B) break;
+        for (int c = tid; c < LAa; c += kThreads) {
+            p.ACT_A[(size_t)b * LAa + c] = sA[r * LA + c];
+            p.DZ_A[(size_t)b * LAa + c] = sZ[r * LA + c];
+        }
+        for (int c = tid; c < LAc; c += kThreads) {
+            p.ACT_C[(size_t)b * LAc + c] = sA[r * LA + LAa + c];
+            p.DZ_C[(size_t)b * LAc + c] = sZ[r * LA + LAa + c];
+        }
+        if (tid < kXStride) p.X[(size_t)b * kXStride + tid] = sX[r * kXStride + tid];
+        if (tid < 2) p.DOUT[(size_t)b * 2 + tid] = sV[r * kRowVals + 6 + tid];
+    }
+}
+
+// torch.optim.Adam (fused implementation's arithmetic): exp_avg = lerp(exp_avg, g, 1-b1); exp_avg_sq = b2 v + (1-b2) g^2;
+// p -= (lr / bc1) * exp_avg / (sqrt(exp_avg_sq) / sqrt(bc2) + eps)
+struct AdamCoef {
+    float lr_bc1, inv_sqrt_bc2, one_m_b1, b2, one_m_b2, eps;
+};
+__device__ __forceinline__ AdamCoef adam_coef(const StepParams &p, int t) {
+    AdamCoef c;
+    const double bc1 = 1.0 - pow((double)p.beta1, (double)t), bc2 = 1.0 - pow((double)p.beta2, (double)t);
+    c.lr_bc1 = (float)((double)p.lr / bc1);
+    c.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    c.one_m_b1 = 1.0f - p.beta1; c.b2 = p.beta2; c.one_m_b2 = 1.0f - p.beta2; c.eps = p.eps;
+    return c;
+}
+__device__ __forceinline__ float adam_update(const AdamCoef &c, float g, float theta, float &m, float &v) {
+    m = m + (g - m) * c.one_m_b1;
+    v = c.b2 * v + c.one_m_b2 * g * g;
+    return theta - c.lr_bc1 * m / (sqrtf(v) * c.inv_sqrt_bc2 + c.eps);
+}
+
+__global__ void __launch_bounds__(kThreads) ppo_wgrad_kernel(const StepParams p) {
+    __shared__ float sD[kBk][kTile + 4];   // dZ[b][n0 + .]
+    __shared__ float sI[kBk][kTile + 4];   // input[b][k0 + .]
+    __shared__ bool is_last;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;   // tx: k direction, ty: n direction
+    int li = 0;
+    while (li + 1 < p.n_layers && (int)blockIdx.x >= p.layer[li + 1].tile0) ++li;
+    const LayerDesc L = p.layer[li];
+    const int t_in = blockIdx.x - L.tile0;
+    const int n0 = (t_in / L.tk) * kTile, k0 = (t_in % L.tk) * kTile;
+    const int B = p.B;
+    const float *dz; int dz_stride;
+    if (L.dz_col < 0) { dz = p.DOUT + L.net; dz_stride = 2; }
+    else if (L.net == 0) { dz = p.DZ_A + L.dz_col; dz_stride = p.act.LA; }
+    else { dz = p.DZ_C + L.dz_col; dz_stride = p.cri.LA; }
+    const float *in; int in_stride;
+    if (L.in_col < 0) { in = p.X + L.x_col; in_stride = kXStride; }
+    else if (L.net == 0) { in = p.ACT_A + L.in_col; in_stride = p.act.LA; }
+    else { in = p.ACT_C + L.in_col; in_stride = p.cri.LA; }
+
+    float acc[4][4], accb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        accb[i] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    }
+    for (int bb = 0; bb < B; bb += kBk) {
+        for (int j = tid; j < kBk * kTile; j += kThreads) {
+            const int r = j / kTile, c = j % kTile, b = bb + r;
+            sD[r][c] = (b < B && n0 + c < L.N) ? dz[(size_t)b * dz_stride + n0 + c] : 0.0f;
+            sI[r][c] = (b < B && k0 + c < L.K) ? in[(size_t)b * in_stride + k0 + c] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < kBk; ++r) {
+            const float4 d = *reinterpret_cast<const float4 *>(&sD[r][ty * 4]);
+            const float4 a = *reinterpret_cast<const float4 *>(&sI[r][tx * 4]);
+            const float dv[4] = {d.x, d.y, d.z, d.w}, av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                accb[i] += dv[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dv[i], av[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+
+    const int t = *p.step_dev + 1;
+    const AdamCoef c = adam_coef(p, t);
+    auto apply = [&](int idx, int idx_t, float g) {
+        if (p.grad_out) { p.grad_out[idx] = g; return; }
+        float m = p.m[idx], v = p.v[idx];
+        const float th = adam_update(c, g, p.theta[idx], m, v);
+        p.m[idx] = m; p.v[idx] = v; p.theta[idx] = th; p.theta_t[idx_t] = th;
+    };
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty * 4 + i;
+        if (n >= L.N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + tx * 4 + j;
+            if (k < L.K) apply(L.w_off + n * L.K + k, L.w_off + k * L.N + n, acc[i][j]);
+        }
+        if (k0 == 0 && tx == 0) apply(L.b_off + n, L.b_off + n, accb[i]);
+    }
+
+    // the last CTA to finish closes the step: a_std_log, step counter, the next ring row, the accumulators
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(p.ticket, 1u) == (unsigned)p.n_tiles - 1u;
+    __syncthreads();
+    if (is_last && tid == 0) {
+        __threadfence();
+        const float g = *reinterpret_cast<volatile float *>(p.g_astd);
+        apply(p.n_theta - 1, p.n_theta - 1, g);
+        *p.g_astd = 0.0f;
+        *p.ticket = 0u;
+        float *nxt = p.loss_ring + (size_t)((*p.step_dev + 1) % p.ring_len) * 4;
+        nxt[0] = nxt[1] = nxt[2] = nxt[3] = 0.0f;
+        *p.step_dev = t;
+    }
+}
+
+__global__ void ppo_transpose_kernel(StepParams p) {
+    for (int li = 0; li < p.n_layers; ++li) {
+        const LayerDesc L = p.layer[li];
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L.N * L.K; j += gridDim.x * blockDim.x) {
+            const int n = j / L.K, k = j % L.K;
+            p.theta_t[L.w_off + k * L.N + n] = p.theta[L.w_off + j];
+        }
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L.N; j += gridDim.x * blockDim.x) p.theta_t[L.b_off + j] = p.theta[L.b_off + j];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.theta_t[p.n_theta - 1] = p.theta[p.n_theta - 1];
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static bool fill_net(const pime_actor_config &c, int theta_off, NetDims &d) {
+    tc::PackLayout L;
+    if (!tc::make_pack_layout(c, L)) return false;
+    d.kind = c.kind; d.S = c.state_dim; d.H = c.mid_dim;
+    d.So = c.kind == PIME_ACTOR_MODULAR ? c.state_dim - c.integrator_dim : c.state_dim;
+    d.LA = c.kind == PIME_ACTOR_MODULAR ? 4 * c.mid_dim : 3 * c.mid_dim;
+    d.theta_off = theta_off;
+    for (int j = 0; j < 12; ++j) d.src[j] = L.src[j];
+    return true;
+}
+
+static void add_layer(StepParams &p, int net, const NetDims &d, int N, int K, int w, int b, int dz_col, int in_col, int x_col) {
+    LayerDesc &L = p.layer[p.n_layers++];
+    L.net = net; L.N = N; L.K = K; L.w_off = d.theta_off + d.src[w]; L.b_off = d.theta_off + d.src[b];
+    L.dz_col = dz_col; L.in_col = in_col; L.x_col = x_col;
+    L.tn = (N + kTile - 1) / kTile; L.tk = (K + kTile - 1) / kTile;
+    L.tile0 = p.n_tiles;
+    p.n_tiles += L.tn * L.tk;
+}
+
+static void add_net_layers(StepParams &p, int net, const NetDims &d) {
+    const int H = d.H;
+    if (d.kind == PIME_ACTOR_MODULAR) {
+        add_layer(p, net, d, H, d.So, 0, 1, 0, -1, 0);                      // other_net.0
+        add_layer(p, net, d, H / 2, H, 2, 3, 2 * H, 0, 0);                  // other_net.2
+        add_layer(p, net, d, H, d.S - d.So, 4, 5, H, -1, d.So);             // integrator_net.0
+        add_layer(p, net, d, H / 2, H, 6, 7, 2 * H + H / 2, H, 0);          // integrator_net.2
+        add_layer(p, net, d, H, H, 8, 9, 3 * H, 2 * H, 0);                  // net.0
+        add_layer(p, net, d, 1, H, 10, 11, -1, 3 * H, 0);                   // net.2
+    } else {
+        add_layer(p, net, d, H, d.S, 0, 1, 0, -1, 0);
+        add_layer(p, net, d, H, H, 2, 3, H, 0, 0);
+        add_layer(p, net, d, H, H, 4, 5, 2 * H, H, 0);
+        add_layer(p, net, d, 1, H, 6, 7, -1, 2 * H, 0);
+    }
+}
+
+static int fill_params(const pime_ppo_args *a, StepParams &p) {
+    PIME_REQUIRE(a && a->actor, "null ppo args / actor config");
+    PIME_REQUIRE(a->actor->kind == PIME_ACTOR_PLAIN || a->actor->kind == PIME_ACTOR_MODULAR, "actor kind");
+    p = StepParams{};
+    pime_actor_config cc{PIME_CRITIC_ADV, a->actor->state_dim, a->actor->mid_dim, 0};
+    PIME_REQUIRE(fill_net(*a->actor, 0, p.act), "unsupported actor dimensions");
+    const int64_t pa = pime_actor_param_count(a->actor), pc = pime_actor_param_count(&cc);
+    PIME_REQUIRE(fill_net(cc, (int)pa, p.cri), "unsupported critic dimensions");
+    p.n_theta = (int)(pa + pc + 1);
+    add_net_layers(p, 0, p.act);
+    add_net_layers(p, 1, p.cri);
+    p.theta = a->theta; p.theta_t = a->theta_t; p.m = a->adam_m; p.v = a->adam_v; p.grad_out = a->grad_out;
+    return PIME_OK;
+}
+
+static int64_t work_floats_per_row(const StepParams &p) { return kXStride + 2 * (int64_t)(p.act.LA + p.cri.LA) + 2; }
+
+template <int R> static int launch_rows(const StepParams &p, cudaStream_t s) {
+    const size_t smem = sizeof(float) * (size_t)(R * (kXStride + 2 * (p.act.LA + p.cri.LA) + kRowVals) + 8);
+    auto kern = ppo_rows_kernel<R>;
+    PIME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(p.B + R - 1) / R, kThreads, smem, s>>>(p);
+    PIME_LAUNCH_CHECK();
+    return PIME_OK;
+}
+
+}  // namespace ppo
+}  // namespace pime
+
+using namespace pime;
+
+extern "C" {
+
+int64_t pime_ppo_theta_count(const pime_actor_config *actor) {
+    if (!actor) return -1;
+    pime_actor_config cc{PIME_CRITIC_ADV, actor->state_dim, actor->mid_dim, 0};
+    const int64_t pa = pime_actor_param_count(actor), pc = pime_actor_param_count(&cc);
+    return pa < 0 || pc < 0 ? -1 : pa + pc + 1;
+}
+
+int64_t pime_ppo_work_floats(const pime_actor_config *actor, int32_t batch) {
+    ppo::StepParams p;
+    pime_ppo_args a{};
+    a.actor = actor;
+    if (!actor || ppo::fill_params(&a, p) != PIME_OK) return -1;
+    return ppo::work_floats_per_row(p) * (int64_t)batch;
+}
+
+int pime_ppo_transpose(const pime_actor_config *actor, const float *theta, float *theta_t, void *stream) {
+    PIME_REQUIRE(actor && theta && theta_t, "null pointer");
+    ppo::StepParams p;
+    pime_ppo_args a{};
+    a.actor = actor; a.theta = const_cast<float *>(theta); a.theta_t = theta_t;
+    if (int rc = ppo::fill_params(&a, p)) return rc;
+    if (int rc = require_device()) return rc;
+    ppo::ppo_transpose_kernel<<<kNumSMs, 256, 0, (cudaStream_t)stream>>>(p);
+    PIME_LAUNCH_CHECK();
+    return PIME_OK;
+}
+
+int pime_ppo_step(const pime_ppo_args *a, void *stream) {
+    ppo::StepParams p;
+    if (int rc = ppo::fill_params(a, p)) return rc;
+    PIME_REQUIRE(a->theta && a->theta_t && a->state && a->work, "null theta / theta_t / state / work");
+    PIME_REQUIRE(a->grad_out || (a->adam_m && a->adam_v), "Adam moments are required unless grad_out is given");
+    PIME_REQUIRE(a->buf_state && a->buf_action && a->buf_r_sum && a->buf_logprob && a->buf_advantage && a->idx, "null replay tensor");
+    PIME_REQUIRE(a->batch >= 2 && a->batch <= (1 << 20), "batch must be in [2, 2^20]");
+    PIME_REQUIRE(a->loss_ring && a->ring_len >= 2, "loss ring");
+    if (int rc = require_device()) return rc;
+    p.buf_state = a->buf_state; p.buf_action = a->buf_action; p.buf_r_sum = a->buf_r_sum; p.buf_logprob = a->buf_logprob;
+    p.buf_adv = a->buf_advantage; p.idx = a->idx; p.B = a->batch;
+    p.ratio_clip = a->ratio_clip; p.lambda_entropy = a->lambda_entropy;
+    p.lr = a->lr; p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps;
+    p.step_dev = (int *)a->state; p.ticket = (unsigned *)a->state + 1; p.g_astd = (float *)a->state + 2;
+    p.loss_ring = a->loss_ring; p.ring_len = a->ring_len;
+    const int64_t B = a->batch;
+    float *w = a->work;
+    p.X = w; w += B * ppo::kXStride;
+    p.ACT_A = w; w += B * p.act.LA;
+    p.DZ_A = w; w += B * p.act.LA;
+    p.ACT_C = w; w += B * p.cri.LA;
+    p.DZ_C = w; w += B * p.cri.LA;
+    p.DOUT = w;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int R = B <= 128 ? 2 : (B <= 256 ? 4 : 8);   // ~64 CTAs at the reference's batch sizes; weights stream once per CTA
+    int rc = R == 2 ? ppo::launch_rows<2>(p, s) : (R == 4 ? ppo::launch_rows<4>(p, s) : ppo::launch_rows<8>(p, s));
+    if (rc) return rc;
+    ppo::ppo_wgrad_kernel<<<p.n_tiles, ppo::kThreads, 0, s>>>(p);
+    PIME_LAUNCH_CHECK();
+    return PIME_OK;
+}
+
+}  // extern "C"

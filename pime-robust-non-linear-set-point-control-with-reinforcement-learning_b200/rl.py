@@ -202,6 +202,82 @@ class CriticAdv(nn.Module):
             p.requires_grad = False
 
 
+# ====================================================================================================== fused learner
+class FusedLearner:
+    """The two-launch PPO minibatch step of libpime_b200 (pime_ppo_step, csrc/learner.cu): flat fp32 copies of the actor,
+    the critic and a_std_log (+ their transposes and the Adam moments), loaded from the torch modules before a round of
+    minibatch steps and stored back after it.  The moments and the step count persist across update_net calls like the
+    state of the torch optimizer they replace (agent.py:56-58)."""
+
+    RING = 4096
+
+    def __init__(self, act, cri, state_dim, net_dim, device):
+        import ctypes as C
+        self.C, self.L = C, V.L
+        D = getattr(act, "other_dim", None)
+        self.kind = act.kind
+        self.cfg = V.L.ActorConfig(kind=V.ActorPack.KIND[act.kind], state_dim=state_dim, mid_dim=net_dim,
+                                   integrator_dim=state_dim - D if D is not None else 0)
+        n = int(V.L.lib().pime_ppo_theta_count(C.byref(self.cfg)))
+        if n < 0:
+            raise ValueError("unsupported network dimensions for the fused learner")
+        self.device = device
+        self.theta, self.theta_t, self.m, self.v = (torch.zeros(n, dtype=torch.float32, device=device) for _ in range(4))
+        self.state = torch.zeros(4, dtype=torch.int32, device=device)
+        self.loss_ring = torch.zeros((self.RING, 4), dtype=torch.float32, device=device)
+        self.work = None
+        self.steps = 0          # host mirror of the device step count
+        self._keys = (V.ActorPack.KEYS[act.kind], V.ActorPack.KEYS["critic"])
+
+    @staticmethod
+    def eligible(agent, batch_size):
+        """Everything trainable (the frozen_* / fix-K variants keep the autograd step), one action, single process."""
+        if _dist_on() or agent.act.kind not in ("plain", "modular") or not 2 <= batch_size <= agent.fused_max_batch:
+            return False
+        named = list(agent.act.named_parameters()) + list(agent.cri.named_parameters())
+        return all(p.requires_grad or n == "priorK" for n, p in named) and agent.act.a_std_log.numel() == 1
+
+    def _tensors(self, act, cri):
+        sa, sc = dict(act.named_parameters()), dict(cri.named_parameters())
+        return [sa[k] for k in self._keys[0]] + [sc[k] for k in self._keys[1]] + [act.a_std_log]
+
+    def load(self, act, cri):
+        with torch.no_grad():
+            torch.cat([t.detach().reshape(-1) for t in self._tensors(act, cri)], out=self.theta)
+        self.L.check(self.L.lib().pime_ppo_transpose(self.C.byref(self.cfg), self.L.ptr(self.theta), self.L.ptr(self.theta_t),
+                                                     self.L.stream_ptr()))
+
+    def store(self, act, cri):
+        with torch.no_grad():
+            o = 0
+            for t in self._tensors(act, cri):
+                t.copy_(self.theta[o:o + t.numel()].view_as(t))
+                o += t.numel()
+
+    def step(self, data, idx, agent, grad_out=None):
+        """One minibatch step on rows ``idx`` of data = (state, action, r_sum, logprob, advantage)."""
+        C, L = self.C, self.L
+        state, action, r_sum, logprob, advantage = data
+        B = int(idx.numel())
+        need = int(L.lib().pime_ppo_work_floats(C.byref(self.cfg), C.c_int32(B)))
+        if self.work is None or self.work.numel() < need:
+            self.work = torch.empty(need, dtype=torch.float32, device=self.device)
+        grp = agent.optimizer.param_groups[0]
+        a = L.PpoArgs(actor=C.pointer(self.cfg), theta=L.ptr(self.theta), theta_t=L.ptr(self.theta_t), adam_m=L.ptr(self.m),
+                      adam_v=L.ptr(self.v), grad_out=L.ptr(grad_out), buf_state=L.ptr(state), buf_action=L.ptr(action),
+                      buf_r_sum=L.ptr(r_sum), buf_logprob=L.ptr(logprob), buf_advantage=L.ptr(advantage), idx=L.ptr(idx),
+                      batch=B, ratio_clip=agent.ratio_clip, lambda_entropy=agent.lambda_entropy, lr=grp["lr"],
+                      beta1=grp["betas"][0], beta2=grp["betas"][1], eps=grp["eps"], state=L.ptr(self.state),
+                      work=L.ptr(self.work), loss_ring=L.ptr(self.loss_ring), ring_len=self.RING)
+        L.check(L.lib().pime_ppo_step(C.byref(a), L.stream_ptr()))
+        self.steps += 1
+
+    def losses(self, first, count):
+        """Rows [first, first + count) of the loss ring -> [count, 4] (united, actor, critic, entropy)."""
+        rows = torch.arange(first, first + count, device=self.device) % self.RING
+        return self.loss_ring[rows]
+
+
 # ====================================================================================================== replay buffer
 class ReplayBuffer:
     """On-policy part of replay.py:238-379 with the storage in HBM.
@@ -300,6 +376,9 @@ class AgentPPO:
         self.use_cuda_graph = True      # record the minibatch step into a CUDA graph when it is launch bound
         self.graph_max_batch = 8192
         self.graph_steps = 4            # minibatch steps per recorded graph
+        self.use_fused_learner = True   # pime_ppo_step (two launches per minibatch) when FusedLearner.eligible
+        self.fused_max_batch = 4096     # beyond it the cuBLAS autograd step is faster than the fp32 SIMT kernels
+        self._fused = None
 
     # ---- construction
     def _make_actor(self, net_dim, state_dim, action_dim, **kw):
@@ -468,6 +547,9 @@ class AgentPPO:
             self.optimizer.step()
             out.copy_(torch.stack([obj_united.detach(), obj_actor.detach(), obj_critic.detach(), obj_entropy.detach()]))
 
+        if self.use_fused_learner and iters and FusedLearner.eligible(self, batch_size):
+            return self._update_fused(data, buf_len, batch_size, iters, repeat_times)
+
         sums = torch.zeros(4, device=self.device)
         last = torch.zeros(4, device=self.device)
         use_graph = self.use_cuda_graph and iters >= 8 and batch_size <= self.graph_max_batch and not _dist_on()
@@ -500,6 +582,28 @@ class AgentPPO:
             logger.record("train/entropy_losses", e)
             return float(last[1]), float(last[2])
         return 0.0, 0.0
+
+    def _update_fused(self, data, buf_len, batch_size, iters, repeat_times):
+        """The minibatch loop of agent.py:635-658 on the fused kernels: index draw (torch) + two launches per step."""
+        f = self._fused
+        if f is None or f.kind != self.act.kind:
+            f = self._fused = FusedLearner(self.act, self.cri, self.state_dim, self.net_dim, self.device)
+        f.load(self.act, self.cri)
+        data = (data[0].contiguous(),) + tuple(t.reshape(-1).contiguous() for t in data[1:])   # [L, S], then four [L] columns
+        first = f.steps
+        for _ in range(iters):
+            idx = torch.randint(buf_len, size=(batch_size,), device=self.device)
+            f.step(data, idx, self)
+        f.store(self.act, self.cri)
+        self._n_updates += int(repeat_times)
+        keep = min(iters, f.RING - 1)
+        rows = f.losses(first + iters - keep, keep)
+        u, a, c, e = rows.mean(0).tolist()
+        logger.record("train/united_loss", u)
+        logger.record("train/actor_loss", a)
+        logger.record("train/critic_loss", c)
+        logger.record("train/entropy_losses", e)
+        return float(rows[-1, 1]), float(rows[-1, 2])
 
     def _graphed_step(self, minibatch, data, buf_len, batch_size):
         """One PPO minibatch (index draw, gather, forward, backward, Adam) recorded ONCE into a CUDA graph and replayed:

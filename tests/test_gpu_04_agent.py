@@ -190,6 +190,7 @@ def test_cuda_graph_minibatch_step_is_transparent():
         agent = R.AgentResidualIntegratorModularPPO()
         agent.learning_rate = 3e-4
         agent.use_cuda_graph = mode
+        agent.use_fused_learner = False          # this test is about the autograd step (the path of frozen / distributed runs)
         agent.init(32, env.state_dim, env.action_dim, env.n_integrator)
         agent.init_residual({"init_K": env.K.reshape(-1, 1)})
         buf = R.ReplayBuffer(n * env.max_step, env.state_dim, 1, True, False, True, num_envs=n)
@@ -236,3 +237,138 @@ def test_examples_train_py_runs_the_reference_command_line(tmp_path):
     assert any(f.endswith("final_model/actor.pth") for f in found) and any(f.endswith("final_model/staircase.npz") for f in found)
     z = np.load([f for f in found if f.endswith("final_model/staircase.npz")][0])
     assert z["agent.ys"].shape == (250, 32) and z["linear.ys"].shape == (250, 32) and np.isfinite(z["agent.totals"]).all()
+
+
+# ------------------------------------------------------------------------------------------------ fused learner kernels
+def _fused_setup(g, tag, lr=3e-4):
+    import pime_b200.rl as R
+    agent = _agent_from_fixture(g, tag)
+    agent.optimizer = torch.optim.Adam([{"params": agent.act.parameters(), "lr": lr}, {"params": agent.cri.parameters(), "lr": lr}])
+    dev = agent.device
+    data = tuple(torch.as_tensor(g[f"{tag}.{k}"]).to(dev).reshape(len(g[f"{tag}.state"]), -1) for k in
+                 ("state", "action", "r_sum", "logprob", "adv_gae"))
+    data = (data[0].contiguous(),) + tuple(t.reshape(-1).contiguous() for t in data[1:])
+    f = R.FusedLearner(agent.act, agent.cri, agent.state_dim, agent.net_dim, dev)
+    f.load(agent.act, agent.cri)
+    return agent, f, data, torch.as_tensor(g[f"{tag}.idx"]).to(dev)
+
+
+def _split(f, agent, flat):
+    out, o = {}, 0
+    names = [k for k in f._keys[0]] + ["cri." + k for k in f._keys[1]] + ["a_std_log"]
+    for name, t in zip(names, f._tensors(agent.act, agent.cri)):
+        out[name] = flat[o:o + t.numel()].view_as(t).cpu().numpy()
+        o += t.numel()
+    return out
+
+
+@pytest.mark.parametrize("tag", ["modular", "plain"])
+def test_fused_ppo_kernels_match_the_reference_gradients_and_adam_step(golden, tag):
+    """pime_ppo_step against the reference's own numbers (oracle/gen_golden.py:gen_ppo: agent.py:635-658 run on a fixed
+    index set): the four objectives (2e-5), every gradient (1e-4 relative) and the parameters after ONE Adam step (1e-5)."""
+    g = golden("ppo")
+    agent, f, data, idx = _fused_setup(g, tag)
+    grad = torch.zeros_like(f.theta)
+    f.step(data, idx, agent, grad_out=grad)                                    # gradient-only mode: theta untouched
+    np.testing.assert_allclose(f.losses(0, 1)[0, [1, 2, 0, 3]].cpu().numpy(), g[f"{tag}.losses"], rtol=2e-5, atol=1e-6)
+    for name, got in _split(f, agent, grad).items():
+        np.testing.assert_allclose(got, g[f"{tag}.grad.{name}"], rtol=1e-4, atol=1e-6, err_msg=name)
+    before = f.theta.clone()
+    f.store(agent.act, agent.cri)
+    assert all(torch.equal(a, b) for a, b in zip(_split_t(f, agent, before), f._tensors(agent.act, agent.cri)))
+
+    agent, f, data, idx = _fused_setup(g, tag)                                 # fresh moments: the fused Adam step
+    f.step(data, idx, agent)
+    f.store(agent.act, agent.cri)
+    assert int(f.state[0]) == 1 and float(f.state.view(torch.float32)[2]) == 0.0 and int(f.state[1]) == 0
+    for k in g.files:
+        for net, pre in ((agent.act, f"{tag}.act1."), (agent.cri, f"{tag}.cri1.")):
+            if k.startswith(pre):
+                np.testing.assert_allclose(net.state_dict()[k[len(pre):]].cpu().numpy(), g[k], rtol=1e-5, atol=1e-6, err_msg=k)
+    # the transposed copy the forward pass reads follows the update
+    w = agent.cri.net[2].weight
+    o = sum(t.numel() for t in f._tensors(agent.act, agent.cri)[:len(f._keys[0]) + 2])
+    assert torch.equal(f.theta_t[o:o + w.numel()].view(w.shape[1], w.shape[0]).t(), w)
+
+
+def _split_t(f, agent, flat):
+    o, out = 0, []
+    for t in f._tensors(agent.act, agent.cri):
+        out.append(flat[o:o + t.numel()].view_as(t))
+        o += t.numel()
+    return out
+
+
+@pytest.mark.parametrize("kind,S,H,B", [("modular", 4, 256, 256), ("modular", 3, 128, 128), ("plain", 30, 256, 200),
+                                        ("plain", 3, 64, 37), ("modular", 4, 32, 1000)])
+def test_fused_ppo_steps_track_the_autograd_path(kind, S, H, B):
+    """Five consecutive minibatch steps (ragged batches included) from the same start and the same index draws: the fused
+    kernels and the torch autograd + torch.optim.Adam step stay together (fp32, different summation order only)."""
+    import pime_b200.rl as R
+    torch.manual_seed(3)
+    agents = []
+    for _ in range(2):
+        agent = R.AgentResidualIntegratorModularPPO() if kind == "modular" else R.AgentResidualPPO()
+        agent.init(H, S, 1, 1) if kind == "modular" else agent.init(H, S, 1)
+        with torch.no_grad():
+            agent.act.net[-1].weight.normal_(0, 0.1)
+        agents.append(agent)
+    a, b = agents
+    b.act.load_state_dict(a.act.state_dict())
+    b.cri.load_state_dict(a.cri.state_dict())
+    L = 3000
+    state = torch.randn(L, S, device="cuda") * 2
+    action = torch.randn(L, device="cuda")
+    r_sum = torch.randn(L, device="cuda") * 3 - 1
+    logprob = -(torch.randn(L, device="cuda").pow(2) * 0.5 + a.act.a_std_log.item() + a.act.sqrt_2pi_log)
+    adv = torch.randn(L, device="cuda")
+    data = (state, action, r_sum, logprob, adv)
+    f = R.FusedLearner(a.act, a.cri, S, H, a.device)
+    f.load(a.act, a.cri)
+    params = [p for grp in b.optimizer.param_groups for p in grp["params"]]
+    for it in range(5):
+        idx = torch.randint(L, size=(B,), device="cuda")
+        f.step(data, idx, a)
+        oa, oc, ou, oe = b.ppo_objectives(state[idx], action[idx].unsqueeze(1), r_sum[idx], logprob[idx], adv[idx])
+        b.optimizer.zero_grad(set_to_none=False)
+        ou.backward()
+        b.optimizer.step()
+        np.testing.assert_allclose(f.losses(it, 1)[0].cpu().numpy(), [ou.item(), oa.item(), oc.item(), oe.item()], rtol=1e-4, atol=1e-5)
+    f.store(a.act, a.cri)
+    lr = b.optimizer.param_groups[0]["lr"]
+    for (n1, p1), (n2, p2) in zip(list(a.act.named_parameters()) + list(a.cri.named_parameters()),
+                                  list(b.act.named_parameters()) + list(b.cri.named_parameters())):
+        if n1 == "priorK":
+            continue
+        # an Adam step moves a weight by at most ~lr whatever the gradient's size: five steps agree to a fraction of one
+        d = (p1 - p2).detach().abs()
+        assert float(d.max()) <= 0.6 * lr and float(d.mean()) <= 0.02 * lr, n1
+
+
+def test_update_net_takes_the_fused_path_and_matches_autograd():
+    import pime_b200.rl as R
+    res = []
+    n = 256
+    for fused in (True, False):
+        torch.manual_seed(11)
+        env = _make(WT, n)
+        agent = R.AgentResidualIntegratorModularPPO()
+        agent.init(64, env.state_dim, env.action_dim, env.n_integrator)
+        agent.use_fused_learner = fused
+        agent.use_cuda_graph = False             # eager autograd step: the same index draws as the fused loop
+        agent.init_residual({"init_K": env.K.reshape(-1, 1)})
+        buf = R.ReplayBuffer(n * env.max_step, env.state_dim, 1, True, False, True, num_envs=n)
+        steps = agent.explore_env(env, buf, n * env.max_step, 1.0, 0.99)
+        torch.manual_seed(12)
+        out = agent.update_net(buf, steps, batch_size=256, repeat_times=1)     # 200 minibatch steps
+        assert (agent._fused is not None) == fused
+        res.append((out, {k: v.clone() for k, v in agent.act.state_dict().items()}, {k: v.clone() for k, v in agent.cri.state_dict().items()},
+                    dict(R.logger.values)))
+    (o1, a1, c1, l1), (o2, a2, c2, l2) = res
+    for k in ("train/united_loss", "train/actor_loss", "train/critic_loss", "train/entropy_losses"):
+        np.testing.assert_allclose(l1[k], l2[k], rtol=5e-3, atol=1e-4, err_msg=k)
+    lr = 1e-4
+    for d1, d2 in ((a1, a2), (c1, c2)):
+        for k in d1:
+            assert float((d1[k] - d2[k]).abs().max()) <= 3 * lr, k        # 200 Adam steps of 1e-4 each: the same trajectory
+            assert float((d1[k] - d2[k]).abs().mean()) <= 0.05 * lr, k
