@@ -290,8 +290,9 @@ int pime_wt_rollout_host_f32(const pime_wt_config *cfg, int64_t n, const pime_wt
  *   obj_critic  = SmoothL1(critic(state), r_sum)
  *   obj_united  = obj_actor + obj_critic / (r_sum.std() + 1e-5);  Adam step on actor, critic and a_std_log
  *
- * theta = [actor parameters | critic parameters | a_std_log], each net in state_dict order (pime_actor_param_count
- * floats; the critic is CriticAdv with the actor's S and H); theta_t holds every weight matrix transposed
+ * theta = [actor parameters | pad | critic parameters | a_std_log], each net in state_dict order (pime_actor_param_count
+ * floats; the critic is CriticAdv with the actor's S and H; its offset, a multiple of 4 floats, the offset of
+ * a_std_log and the total come from pime_ppo_theta_layout); theta_t holds every weight matrix transposed
  * (pime_ppo_transpose; kept up to date by the step).  state: device int32[4], zero-initialised, owned by the
  * library between steps (Adam step count, a ticket, the a_std_log gradient accumulator).  loss_ring: device
  * float[ring_len][4], zero-initialised; step t (0-based count before the call) adds the means of (obj_united,
@@ -315,6 +316,7 @@ typedef struct pime_ppo_args {
 } pime_ppo_args;
 
 int64_t pime_ppo_theta_count(const pime_actor_config *actor);
+int pime_ppo_theta_layout(const pime_actor_config *actor, int64_t *out3); /* critic offset, a_std_log offset, total */
 int64_t pime_ppo_work_floats(const pime_actor_config *actor, int32_t batch);
 int pime_ppo_transpose(const pime_actor_config *actor, const float *theta, float *theta_t, void *stream);
 int pime_ppo_step(const pime_ppo_args *args, void *stream);

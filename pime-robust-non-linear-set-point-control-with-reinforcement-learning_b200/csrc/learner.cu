@@ -5,9 +5,10 @@
 //   ppo_rows_kernel   one CTA per R minibatch rows: gather the rows, actor and critic forward (fp32, activations in
 //                     shared memory), the clipped-surrogate / entropy / SmoothL1 objectives and their gradients, the
 //                     data-gradient chain through both networks.  Rows are independent, so no grid-wide step exists;
-//                     weights stream from L2 (forward from the transposed copy, backward from the torch layout, so that
-//                     both are coalesced).  Activations and pre-activation gradients go to a scratch buffer.
-//   ppo_wgrad_kernel  one CTA per 64 x 64 tile of a weight matrix: dW = dZ^T . A over the minibatch, bias gradient, and
+//                     a ninth warp streams the hidden-layer weights from L2 through a cp.async.bulk ring (forward from
+//                     the transposed copy, backward from the torch layout, so that thread n / thread k reads its own
+//                     column).  Activations and pre-activation gradients go to a scratch buffer.
+//   ppo_wgrad_kernel  one CTA per 32 x 64 tile of a weight matrix: dW = dZ^T . A over the minibatch (cp.async double-buffered), bias gradient, and
 //                     the Adam update (torch.optim.Adam arithmetic) applied in place to the weights, their transposed
 //                     copy and the moments.  Every gradient element is produced by exactly one thread: no atomics.
 //
@@ -18,11 +19,16 @@
 namespace pime {
 namespace ppo {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;          // compute threads of the rows kernel (one more warp streams the weights)
+constexpr int kRowsThreads = kThreads + 32;
+constexpr int kSlabRows = 16;          // weight rows per streamed slab
+constexpr int kSlabFloats = kSlabRows * 256;
+constexpr int kStages = 4;             // slabs in flight (cp.async.bulk ring)
+constexpr int kMaxPasses = 12;
 constexpr int kMaxLayers = 10;
 constexpr int kXStride = 32;      // gathered state row (S <= 32)
 constexpr int kRowVals = 8;       // per-row scalars in shared memory
-constexpr int kTile = 64;         // weight-gradient tile
+constexpr int kTileN = 32, kTileK = 64;   // weight-gradient tile
 constexpr int kBk = 32;           // minibatch rows per shared-memory stage of the weight-gradient kernel
 
 enum { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2 };
@@ -43,9 +49,17 @@ struct NetDims {
     int src[12];              // offsets of the state_dict tensors inside the net's parameters
 };
 
+struct StreamPass {       // one hidden-layer weight matrix streamed through the shared-memory ring, 16 rows per slab
+    int off;              // offset in theta (backward: torch layout [N][K]) or theta_t (forward: [K][N])
+    int transposed;       // 1: theta_t
+    int rows, cols;
+};
+
 struct StepParams {
     NetDims act, cri;
     int n_layers, n_tiles;
+    int n_passes;
+    StreamPass pass[kMaxPasses];
     LayerDesc layer[kMaxLayers];
     float *theta, *theta_t, *m, *v, *grad_out;
     int n_theta;              // actor + critic + a_std_log
@@ -98,6 +112,86 @@ __device__ __forceinline__ void fwd_layer(const float *in, int in_stride, int K,
     }
 }
 
+// The weight ring: warp 8 streams every hidden-layer matrix of the step, slab by slab (cp.async.bulk, kStages in flight,
+// so the L2 latency is paid once); the 8 compute warps consume the slabs in the same order.
+struct Ring {
+    float *buf;
+    uint64_t *full, *empty;
+    uint32_t st, ph;
+    __device__ __forceinline__ const float *acquire() {
+        tc::mbar_wait(&full[st], ph);
+        return buf + st * kSlabFloats;
+    }
+    __device__ __forceinline__ void release() {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) tc::mbar_arrive(&empty[st]);
+        if (++st == kStages) { st = 0; ph ^= 1; }
+    }
+};
+
+// hidden layer forward through the ring: out[r][n] = act(b[n] + sum_k in[r][k] Wt[k][n]), thread n
+template <int R>
+__device__ __forceinline__ void fwd_ring(Ring &ring, const float *in, int in_stride, int K, const float *__restrict__ bias, int N, int act,
+                                         float *out, int out_stride) {
+    const int n = threadIdx.x;
+    const bool on = n < N;
+    float acc[R];
+    const float b = on ? __ldg(bias + n) : 0.0f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = b;
+    for (int k0 = 0; k0 < K; k0 += kSlabRows) {
+        const float *w = ring.acquire();
+        if (on) {
+#pragma unroll
+            for (int kk = 0; kk < kSlabRows; kk += 4) {
+                const float w0 = w[(kk + 0) * N + n], w1 = w[(kk + 1) * N + n], w2 = w[(kk + 2) * N + n], w3 = w[(kk + 3) * N + n];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float4 a = *reinterpret_cast<const float4 *>(in + r * in_stride + k0 + kk);
+                    acc[r] = fmaf(a.x, w0, acc[r]); acc[r] = fmaf(a.y, w1, acc[r]);
+                    acc[r] = fmaf(a.z, w2, acc[r]); acc[r] = fmaf(a.w, w3, acc[r]);
+                }
+            }
+        }
+        ring.release();
+    }
+    if (on) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[r * out_stride + n] = act_apply(act, acc[r]);
+    }
+}
+
+// hidden layer backward through the ring: dz_in[r][k] = act'(a_in[r][k]) * sum_n dz_out[r][n] W[n][k], thread k (K == kThreads or less)
+template <int R>
+__device__ __forceinline__ void bwd_ring(Ring &ring, const float *dz_out, int dzo_stride, int N, int K, const float *a_in, int a_stride,
+                                         int act_in, float *dz_in, int dzi_stride) {
+    const int k = threadIdx.x;
+    const bool on = k < K;
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0f;
+    for (int n0 = 0; n0 < N; n0 += kSlabRows) {
+        const float *w = ring.acquire();
+        if (on) {
+#pragma unroll
+            for (int nn = 0; nn < kSlabRows; nn += 4) {
+                const float w0 = w[(nn + 0) * K + k], w1 = w[(nn + 1) * K + k], w2 = w[(nn + 2) * K + k], w3 = w[(nn + 3) * K + k];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float4 d = *reinterpret_cast<const float4 *>(dz_out + r * dzo_stride + n0 + nn);
+                    acc[r] = fmaf(d.x, w0, acc[r]); acc[r] = fmaf(d.y, w1, acc[r]);
+                    acc[r] = fmaf(d.z, w2, acc[r]); acc[r] = fmaf(d.w, w3, acc[r]);
+                }
+            }
+        }
+        ring.release();
+    }
+    if (on) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) dz_in[r * dzi_stride + k] = acc[r] * act_grad(act_in, a_in[r * a_stride + k]);
+    }
+}
+
 // Linear(K -> 1): one warp per row
 template <int R>
 __device__ __forceinline__ void fwd_out(const float *in, int in_stride, int K, const float *__restrict__ w, float b, float *out,
@@ -112,33 +206,6 @@ __device__ __forceinline__ void fwd_out(const float *in, int in_stride, int K, c
     }
 }
 
-// dz_in[r][k] = act'(a_in[r][k]) * sum_n dz_out[r][n] W[n][k]; thread k, weights coalesced along k
-template <int R>
-__device__ __forceinline__ void bwd_layer(const float *dz_out, int dzo_stride, int N, const float *__restrict__ W, int K,
-                                          const float *a_in, int a_stride, int act_in, float *dz_in, int dzi_stride) {
-    for (int k = threadIdx.x; k < K; k += kThreads) {
-        float acc[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = 0.0f;
-        for (int n = 0; n + 8 <= N; n += 8) {
-            float w[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = __ldg(W + (size_t)(n + j) * K + k);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float4 d0 = *reinterpret_cast<const float4 *>(dz_out + r * dzo_stride + n);
-                const float4 d1 = *reinterpret_cast<const float4 *>(dz_out + r * dzo_stride + n + 4);
-                acc[r] = fmaf(d0.x, w[0], acc[r]); acc[r] = fmaf(d0.y, w[1], acc[r]);
-                acc[r] = fmaf(d0.z, w[2], acc[r]); acc[r] = fmaf(d0.w, w[3], acc[r]);
-                acc[r] = fmaf(d1.x, w[4], acc[r]); acc[r] = fmaf(d1.y, w[5], acc[r]);
-                acc[r] = fmaf(d1.z, w[6], acc[r]); acc[r] = fmaf(d1.w, w[7], acc[r]);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) dz_in[r * dzi_stride + k] = acc[r] * act_grad(act_in, a_in[r * a_stride + k]);
-    }
-}
-
 // backward of Linear(K -> 1): dz_in[r][k] = act'(a_in[r][k]) * d_out[r] * w[k]
 template <int R>
 __device__ __forceinline__ void bwd_out(const float *d_out, int d_stride, const float *__restrict__ w, int K, const float *a_in,
@@ -150,76 +217,107 @@ __device__ __forceinline__ void bwd_out(const float *d_out, int d_stride, const 
     }
 }
 
+// barrier of the 8 compute warps of the rows kernel (the streaming warp never joins)
+__device__ __forceinline__ void sync_compute() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
+
 __device__ __forceinline__ float block_sum(float v, float *scratch) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
+    sync_compute();
     if (lane == 0) scratch[warp] = v;
-    __syncthreads();
+    sync_compute();
     float s = 0.0f;
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) s += scratch[w];
     return s;
 }
 
-// forward (and its mirror, the data-gradient chain) of one net on R rows held in shared memory
+// forward (and its mirror, the data-gradient chain) of one net on R rows held in shared memory.  Compute warps only; the
+// hidden layers take their weights from the ring in the order fill_passes() lists them.
 template <int R>
-__device__ __forceinline__ void net_forward(const NetDims &d, const float *__restrict__ th, const float *__restrict__ tt, const float *sX,
-                                            float *A, int as, float *out, int out_stride) {
+__device__ __forceinline__ void net_forward(Ring &ring, const NetDims &d, const float *__restrict__ th, const float *__restrict__ tt,
+                                            const float *sX, float *A, int as, float *out, int out_stride) {
     const int H = d.H;
     if (d.kind == PIME_ACTOR_MODULAR) {   // net_residual.py:150-170
         const int Hh = H / 2;
         fwd_layer<R>(sX, kXStride, d.So, tt + d.src[0], th + d.src[1], H, ACT_TANH, A, as);                       // other_net.0
         fwd_layer<R>(sX + d.So, kXStride, d.S - d.So, tt + d.src[4], th + d.src[5], H, ACT_TANH, A + H, as);     // integrator_net.0
-        __syncthreads();
-        fwd_layer<R>(A, as, H, tt + d.src[2], th + d.src[3], Hh, ACT_TANH, A + 2 * H, as);                        // other_net.2
-        fwd_layer<R>(A + H, as, H, tt + d.src[6], th + d.src[7], Hh, ACT_TANH, A + 2 * H + Hh, as);               // integrator_net.2
-        __syncthreads();
-        fwd_layer<R>(A + 2 * H, as, H, tt + d.src[8], th + d.src[9], H, ACT_TANH, A + 3 * H, as);                 // net.0 on cat
-        __syncthreads();
+        sync_compute();
+        fwd_ring<R>(ring, A, as, H, th + d.src[3], Hh, ACT_TANH, A + 2 * H, as);                                  // other_net.2
+        fwd_ring<R>(ring, A + H, as, H, th + d.src[7], Hh, ACT_TANH, A + 2 * H + Hh, as);                         // integrator_net.2
+        sync_compute();
+        fwd_ring<R>(ring, A + 2 * H, as, H, th + d.src[9], H, ACT_TANH, A + 3 * H, as);                           // net.0 on cat
+        sync_compute();
         fwd_out<R>(A + 3 * H, as, H, th + d.src[10], __ldg(th + d.src[11]), out, out_stride);                     // net.2
     } else {                               // plain actor (tanh) / CriticAdv (relu)
         const int act = d.kind == PIME_CRITIC_ADV ? ACT_RELU : ACT_TANH;
         fwd_layer<R>(sX, kXStride, d.S, tt + d.src[0], th + d.src[1], H, act, A, as);
-        __syncthreads();
-        fwd_layer<R>(A, as, H, tt + d.src[2], th + d.src[3], H, act, A + H, as);
-        __syncthreads();
-        fwd_layer<R>(A + H, as, H, tt + d.src[4], th + d.src[5], H, act, A + 2 * H, as);
-        __syncthreads();
+        sync_compute();
+        fwd_ring<R>(ring, A, as, H, th + d.src[3], H, act, A + H, as);
+        sync_compute();
+        fwd_ring<R>(ring, A + H, as, H, th + d.src[5], H, act, A + 2 * H, as);
+        sync_compute();
         fwd_out<R>(A + 2 * H, as, H, th + d.src[6], __ldg(th + d.src[7]), out, out_stride);
     }
-    __syncthreads();
+    sync_compute();
 }
 
 template <int R>
-__device__ __forceinline__ void net_backward(const NetDims &d, const float *__restrict__ th, const float *A, float *Z, int as,
+__device__ __forceinline__ void net_backward(Ring &ring, const NetDims &d, const float *__restrict__ th, const float *A, float *Z, int as,
                                              const float *d_out, int d_stride) {
     const int H = d.H;
     if (d.kind == PIME_ACTOR_MODULAR) {
         const int Hh = H / 2;
         bwd_out<R>(d_out, d_stride, th + d.src[10], H, A + 3 * H, as, ACT_TANH, Z + 3 * H, as);                   // -> dZ(net.0)
-        __syncthreads();
-        bwd_layer<R>(Z + 3 * H, as, H, th + d.src[8], H, A + 2 * H, as, ACT_TANH, Z + 2 * H, as);                 // -> dZ(other_net.2 | integrator_net.2)
-        __syncthreads();
-        bwd_layer<R>(Z + 2 * H, as, Hh, th + d.src[2], H, A, as, ACT_TANH, Z, as);                                // -> dZ(other_net.0)
-        bwd_layer<R>(Z + 2 * H + Hh, as, Hh, th + d.src[6], H, A + H, as, ACT_TANH, Z + H, as);                   // -> dZ(integrator_net.0)
+        sync_compute();
+        bwd_ring<R>(ring, Z + 3 * H, as, H, H, A + 2 * H, as, ACT_TANH, Z + 2 * H, as);                           // net.0 -> dZ(other_net.2 | integrator_net.2)
+        sync_compute();
+        bwd_ring<R>(ring, Z + 2 * H, as, Hh, H, A, as, ACT_TANH, Z, as);                                          // other_net.2 -> dZ(other_net.0)
+        bwd_ring<R>(ring, Z + 2 * H + Hh, as, Hh, H, A + H, as, ACT_TANH, Z + H, as);                             // integrator_net.2 -> dZ(integrator_net.0)
     } else {
         const int act = d.kind == PIME_CRITIC_ADV ? ACT_RELU : ACT_TANH;
         bwd_out<R>(d_out, d_stride, th + d.src[6], H, A + 2 * H, as, act, Z + 2 * H, as);
-        __syncthreads();
-        bwd_layer<R>(Z + 2 * H, as, H, th + d.src[4], H, A + H, as, act, Z + H, as);
-        __syncthreads();
-        bwd_layer<R>(Z + H, as, H, th + d.src[2], H, A, as, act, Z, as);
+        sync_compute();
+        bwd_ring<R>(ring, Z + 2 * H, as, H, H, A + H, as, act, Z + H, as);                                        // net.4
+        sync_compute();
+        bwd_ring<R>(ring, Z + H, as, H, H, A, as, act, Z, as);                                                    // net.2
     }
-    __syncthreads();
+    sync_compute();
 }
 
 template <int R>
-__global__ void __launch_bounds__(kThreads) ppo_rows_kernel(const StepParams p) {
-    extern __shared__ __align__(16) float sm[];
+__global__ void __launch_bounds__(kRowsThreads, 1) ppo_rows_kernel(const StepParams p) {
+    extern __shared__ __align__(128) float sm[];
     const int LAa = p.act.LA, LAc = p.cri.LA, LA = LAa + LAc;
-    float *sX = sm;                         // [R][kXStride]
+    Ring ring;
+    ring.buf = sm;                          // [kStages][kSlabFloats]
+    ring.full = reinterpret_cast<uint64_t *>(sm + kStages * kSlabFloats);
+    ring.empty = ring.full + kStages;
+    ring.st = 0; ring.ph = 0;
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < kStages; ++j) { tc::mbar_init(&ring.full[j], 1); tc::mbar_init(&ring.empty[j], kThreads / 32); }
+        tc::fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x >= kThreads) {          // warp 8: streams every hidden-layer matrix of the step through the ring
+        if (threadIdx.x == kThreads) {
+            uint32_t st = 0, ph = 0;
+            for (int q = 0; q < p.n_passes; ++q) {
+                const StreamPass P = p.pass[q];
+                const float *src = (P.transposed ? p.theta_t : p.theta) + P.off;
+                const uint32_t bytes = (uint32_t)(kSlabRows * P.cols * sizeof(float));
+                for (int r0 = 0; r0 < P.rows; r0 += kSlabRows) {
+                    tc::mbar_wait(&ring.empty[st], ph ^ 1);
+                    tc::mbar_arrive_expect_tx(&ring.full[st], bytes);
+                    tc::bulk_g2s(ring.buf + st * kSlabFloats, src + (size_t)r0 * P.cols, bytes, &ring.full[st]);
+                    if (++st == kStages) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+    float *sX = reinterpret_cast<float *>(ring.empty + kStages);   // [R][kXStride]
     float *sA = sX + R * kXStride;          // [R][LA] activations: actor | critic
     float *sZ = sA + R * LA;                // [R][LA] pre-activation gradients
     float *sV = sZ + R * LA;                // [R][kRowVals]: action, r_sum, logprob_old, advantage, a_avg, value, d_a, d_v
@@ -256,12 +354,12 @@ __global__ void __launch_bounds__(kThreads) ppo_rows_kernel(const StepParams p) 
         sV[tid * kRowVals + 2] = live ? __ldg(p.buf_logprob + i) : 0.0f;
         sV[tid * kRowVals + 3] = live ? __ldg(p.buf_adv + i) : 0.0f;
     }
-    __syncthreads();
+    sync_compute();
 
     const float *thA = p.theta + p.act.theta_off, *ttA = p.theta_t + p.act.theta_off;
     const float *thC = p.theta + p.cri.theta_off, *ttC = p.theta_t + p.cri.theta_off;
-    net_forward<R>(p.act, thA, ttA, sX, sA, LA, sV + 4, kRowVals);
-    net_forward<R>(p.cri, thC, ttC, sX, sA + LAa, LA, sV + 5, kRowVals);
+    net_forward<R>(ring, p.act, thA, ttA, sX, sA, LA, sV + 4, kRowVals);
+    net_forward<R>(ring, p.cri, thC, ttC, sX, sA + LAa, LA, sV + 5, kRowVals);
 
     // objectives and their gradients (agent.py:635-652), one thread per row
     if (tid < R) {
@@ -305,10 +403,10 @@ __global__ void __launch_bounds__(kThreads) ppo_rows_kernel(const StepParams p) 
             atomicAdd(p.g_astd, g_asl);
         }
     }
-    __syncthreads();
+    sync_compute();
 
-    net_backward<R>(p.act, thA, sA, sZ, LA, sV + 6, kRowVals);
-    net_backward<R>(p.cri, thC, sA + LAa, sZ + LAa, LA, sV + 7, kRowVals);
+    net_backward<R>(ring, p.act, thA, sA, sZ, LA, sV + 6, kRowVals);
+    net_backward<R>(ring, p.cri, thC, sA + LAa, sZ + LAa, LA, sV + 7, kRowVals);
 
     // rows -> scratch (inputs of the weight-gradient kernel)
     for (int r = 0; r < R; ++r) {
@@ -346,47 +444,84 @@ __device__ __forceinline__ float adam_update(const AdamCoef &c, float g, float t
     return theta - c.lr_bc1 * m / (sqrtf(v) * c.inv_sqrt_bc2 + c.eps);
 }
 
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    const int bytes = valid ? 16 : 0;   // 0: the 16 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(kThreads) ppo_wgrad_kernel(const StepParams p) {
-    __shared__ float sD[kBk][kTile + 4];   // dZ[b][n0 + .]
-    __shared__ float sI[kBk][kTile + 4];   // input[b][k0 + .]
+    __shared__ __align__(16) float sD[2][kBk][kTileN + 4];   // dZ[b][n0 + .], two stages
+    __shared__ __align__(16) float sI[2][kBk][kTileK + 4];   // input[b][k0 + .]
     __shared__ bool is_last;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;   // tx: k direction, ty: n direction
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;   // tx: 4 columns of k, ty: 2 rows of n
     int li = 0;
     while (li + 1 < p.n_layers && (int)blockIdx.x >= p.layer[li + 1].tile0) ++li;
     const LayerDesc L = p.layer[li];
     const int t_in = blockIdx.x - L.tile0;
-    const int n0 = (t_in / L.tk) * kTile, k0 = (t_in % L.tk) * kTile;
+    const int n0 = (t_in / L.tk) * kTileN, k0 = (t_in % L.tk) * kTileK;
     const int B = p.B;
     const float *dz; int dz_stride;
     if (L.dz_col < 0) { dz = p.DOUT + L.net; dz_stride = 2; }
     else if (L.net == 0) { dz = p.DZ_A + L.dz_col; dz_stride = p.act.LA; }
     else { dz = p.DZ_C + L.dz_col; dz_stride = p.cri.LA; }
-    const float *in; int in_stride;
-    if (L.in_col < 0) { in = p.X + L.x_col; in_stride = kXStride; }
-    else if (L.net == 0) { in = p.ACT_A + L.in_col; in_stride = p.act.LA; }
-    else { in = p.ACT_C + L.in_col; in_stride = p.cri.LA; }
+    const float *in; int in_stride, in_avail;   // in_avail: readable columns of an input row (the products beyond K are dropped)
+    if (L.in_col < 0) { in = p.X + L.x_col; in_stride = kXStride; in_avail = kXStride - L.x_col; }
+    else if (L.net == 0) { in = p.ACT_A + L.in_col; in_stride = p.act.LA; in_avail = L.K; }
+    else { in = p.ACT_C + L.in_col; in_stride = p.cri.LA; in_avail = L.K; }
+    // 16-byte cp.async needs aligned rows: true for every hidden layer; the output layers (dZ = DOUT, stride 2) and the
+    // integrator branch's first layer (input column So of X) take the scalar path -- they are a handful of tiny tiles
+    const bool fast = L.dz_col >= 0 && (L.in_col >= 0 || (L.x_col & 3) == 0);
 
-    float acc[4][4], accb[4];
+    auto fill = [&](int stage, int bb) {
+        if (fast) {
+            {
+                const int r = tid >> 3, c = (tid & 7) * 4, b = bb + r;
+                const bool ok = b < B && n0 + c < L.N;
+                cp_async16(&sD[stage][r][c], ok ? dz + (size_t)b * dz_stride + n0 + c : dz, ok);
+            }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+            for (int h = 0; h < 2; ++h) {
+                const int j = tid + h * kThreads, r = j >> 4, c = (j & 15) * 4, b = bb + r;
+                const bool ok = b < B && k0 + c + 4 <= in_avail;
+                cp_async16(&sI[stage][r][c], ok ? in + (size_t)b * in_stride + k0 + c : in, ok);
+            }
+        } else {
+            for (int j = tid; j < kBk * kTileN; j += kThreads) {
+                const int r = j / kTileN, c = j % kTileN, b = bb + r;
+                sD[stage][r][c] = (b < B && n0 + c < L.N) ? dz[(size_t)b * dz_stride + n0 + c] : 0.0f;
+            }
+            for (int j = tid; j < kBk * kTileK; j += kThreads) {
+                const int r = j / kTileK, c = j % kTileK, b = bb + r;
+                sI[stage][r][c] = (b < B && k0 + c < L.K) ? in[(size_t)b * in_stride + k0 + c] : 0.0f;
+            }
+        }
+        cp_async_commit();
+    };
+
+    float acc[2][4], accb[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
         accb[i] = 0.0f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
     }
-    for (int bb = 0; bb < B; bb += kBk) {
-        for (int j = tid; j < kBk * kTile; j += kThreads) {
-            const int r = j / kTile, c = j % kTile, b = bb + r;
-            sD[r][c] = (b < B && n0 + c < L.N) ? dz[(size_t)b * dz_stride + n0 + c] : 0.0f;
-            sI[r][c] = (b < B && k0 + c < L.K) ? in[(size_t)b * in_stride + k0 + c] : 0.0f;
-        }
+    const int nst = (B + kBk - 1) / kBk;
+    fill(0, 0);
+    for (int it = 0; it < nst; ++it) {
+        const int cur = it & 1;
+        if (it + 1 < nst) { fill(cur ^ 1, (it + 1) * kBk); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
         __syncthreads();
 #pragma unroll 8
         for (int r = 0; r < kBk; ++r) {
-            const float4 d = *reinterpret_cast<const float4 *>(&sD[r][ty * 4]);
-            const float4 a = *reinterpret_cast<const float4 *>(&sI[r][tx * 4]);
-            const float dv[4] = {d.x, d.y, d.z, d.w}, av[4] = {a.x, a.y, a.z, a.w};
+            const float2 d = *reinterpret_cast<const float2 *>(&sD[cur][r][ty * 2]);
+            const float4 a = *reinterpret_cast<const float4 *>(&sI[cur][r][tx * 4]);
+            const float dv[2] = {d.x, d.y}, av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 2; ++i) {
                 accb[i] += dv[i];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dv[i], av[j], acc[i][j]);
@@ -404,8 +539,8 @@ __global__ void __launch_bounds__(kThreads) ppo_wgrad_kernel(const StepParams p)
         p.m[idx] = m; p.v[idx] = v; p.theta[idx] = th; p.theta_t[idx_t] = th;
     };
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int n = n0 + ty * 4 + i;
+    for (int i = 0; i < 2; ++i) {
+        const int n = n0 + ty * 2 + i;
         if (n >= L.N) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -460,7 +595,7 @@ static void add_layer(StepParams &p, int net, const NetDims &d, int N, int K, in
     LayerDesc &L = p.layer[p.n_layers++];
     L.net = net; L.N = N; L.K = K; L.w_off = d.theta_off + d.src[w]; L.b_off = d.theta_off + d.src[b];
     L.dz_col = dz_col; L.in_col = in_col; L.x_col = x_col;
-    L.tn = (N + kTile - 1) / kTile; L.tk = (K + kTile - 1) / kTile;
+    L.tn = (N + kTileN - 1) / kTileN; L.tk = (K + kTileK - 1) / kTileK;
     L.tile0 = p.n_tiles;
     p.n_tiles += L.tn * L.tk;
 }
@@ -482,6 +617,27 @@ static void add_net_layers(StepParams &p, int net, const NetDims &d) {
     }
 }
 
+static void add_pass(StepParams &p, const NetDims &d, int src, bool transposed, int rows, int cols) {
+    StreamPass &q = p.pass[p.n_passes++];
+    q.off = d.theta_off + d.src[src]; q.transposed = transposed ? 1 : 0; q.rows = rows; q.cols = cols;
+}
+// the order in which net_forward / net_backward consume the ring
+static void fill_passes(StepParams &p) {
+    for (int dir = 0; dir < 2; ++dir)
+        for (const NetDims *d : {&p.act, &p.cri}) {
+            const int H = d->H, Hh = H / 2;
+            if (d->kind == PIME_ACTOR_MODULAR) {
+                if (dir == 0) { add_pass(p, *d, 2, true, H, Hh); add_pass(p, *d, 6, true, H, Hh); add_pass(p, *d, 8, true, H, H); }
+                else { add_pass(p, *d, 8, false, H, H); add_pass(p, *d, 2, false, Hh, H); add_pass(p, *d, 6, false, Hh, H); }
+            } else {
+                if (dir == 0) { add_pass(p, *d, 2, true, H, H); add_pass(p, *d, 4, true, H, H); }
+                else { add_pass(p, *d, 4, false, H, H); add_pass(p, *d, 2, false, H, H); }
+            }
+        }
+}
+
+static int64_t critic_offset(int64_t actor_params) { return (actor_params + 3) & ~(int64_t)3; }   // 16-byte aligned for the bulk copies
+
 static int fill_params(const pime_ppo_args *a, StepParams &p) {
     PIME_REQUIRE(a && a->actor, "null ppo args / actor config");
     PIME_REQUIRE(a->actor->kind == PIME_ACTOR_PLAIN || a->actor->kind == PIME_ACTOR_MODULAR, "actor kind");
@@ -489,10 +645,11 @@ static int fill_params(const pime_ppo_args *a, StepParams &p) {
     pime_actor_config cc{PIME_CRITIC_ADV, a->actor->state_dim, a->actor->mid_dim, 0};
     PIME_REQUIRE(fill_net(*a->actor, 0, p.act), "unsupported actor dimensions");
     const int64_t pa = pime_actor_param_count(a->actor), pc = pime_actor_param_count(&cc);
-    PIME_REQUIRE(fill_net(cc, (int)pa, p.cri), "unsupported critic dimensions");
-    p.n_theta = (int)(pa + pc + 1);
+    PIME_REQUIRE(fill_net(cc, (int)critic_offset(pa), p.cri), "unsupported critic dimensions");
+    p.n_theta = (int)(critic_offset(pa) + pc + 1);
     add_net_layers(p, 0, p.act);
     add_net_layers(p, 1, p.cri);
+    fill_passes(p);
     p.theta = a->theta; p.theta_t = a->theta_t; p.m = a->adam_m; p.v = a->adam_v; p.grad_out = a->grad_out;
     return PIME_OK;
 }
@@ -500,10 +657,11 @@ static int fill_params(const pime_ppo_args *a, StepParams &p) {
 static int64_t work_floats_per_row(const StepParams &p) { return kXStride + 2 * (int64_t)(p.act.LA + p.cri.LA) + 2; }
 
 template <int R> static int launch_rows(const StepParams &p, cudaStream_t s) {
-    const size_t smem = sizeof(float) * (size_t)(R * (kXStride + 2 * (p.act.LA + p.cri.LA) + kRowVals) + 8);
+    const size_t smem = sizeof(float) * (size_t)(kStages * kSlabFloats + R * (kXStride + 2 * (p.act.LA + p.cri.LA) + kRowVals) + 8) +
+                        2 * kStages * sizeof(uint64_t);
     auto kern = ppo_rows_kernel<R>;
     PIME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(p.B + R - 1) / R, kThreads, smem, s>>>(p);
+    kern<<<(p.B + R - 1) / R, kRowsThreads, smem, s>>>(p);
     PIME_LAUNCH_CHECK();
     return PIME_OK;
 }
@@ -516,10 +674,19 @@ using namespace pime;
 extern "C" {
 
 int64_t pime_ppo_theta_count(const pime_actor_config *actor) {
-    if (!actor) return -1;
+    int64_t lay[3];
+    return pime_ppo_theta_layout(actor, lay) == PIME_OK ? lay[2] : -1;
+}
+
+int pime_ppo_theta_layout(const pime_actor_config *actor, int64_t *out) {
+    PIME_REQUIRE(actor && out, "null pointer");
     pime_actor_config cc{PIME_CRITIC_ADV, actor->state_dim, actor->mid_dim, 0};
     const int64_t pa = pime_actor_param_count(actor), pc = pime_actor_param_count(&cc);
-    return pa < 0 || pc < 0 ? -1 : pa + pc + 1;
+    PIME_REQUIRE(pa > 0 && pc > 0, "unsupported network dimensions");
+    out[0] = ppo::critic_offset(pa);
+    out[1] = out[0] + pc;
+    out[2] = out[1] + 1;
+    return PIME_OK;
 }
 
 int64_t pime_ppo_work_floats(const pime_actor_config *actor, int32_t batch) {

@@ -218,9 +218,9 @@ class FusedLearner:
         self.kind = act.kind
         self.cfg = V.L.ActorConfig(kind=V.ActorPack.KIND[act.kind], state_dim=state_dim, mid_dim=net_dim,
                                    integrator_dim=state_dim - D if D is not None else 0)
-        n = int(V.L.lib().pime_ppo_theta_count(C.byref(self.cfg)))
-        if n < 0:
-            raise ValueError("unsupported network dimensions for the fused learner")
+        lay = (C.c_int64 * 3)()
+        V.L.check(V.L.lib().pime_ppo_theta_layout(C.byref(self.cfg), lay))
+        self.cri_off, self.astd_off, n = int(lay[0]), int(lay[1]), int(lay[2])
         self.device = device
         self.theta, self.theta_t, self.m, self.v = (torch.zeros(n, dtype=torch.float32, device=device) for _ in range(4))
         self.state = torch.zeros(4, dtype=torch.int32, device=device)
@@ -241,18 +241,31 @@ class FusedLearner:
         sa, sc = dict(act.named_parameters()), dict(cri.named_parameters())
         return [sa[k] for k in self._keys[0]] + [sc[k] for k in self._keys[1]] + [act.a_std_log]
 
+    def _slices(self, act, cri):
+        """(tensor, offset in theta) for every trained tensor: actor from 0, critic from cri_off, a_std_log last."""
+        ts = self._tensors(act, cri)
+        na = len(self._keys[0])
+        out, o = [], 0
+        for i, t in enumerate(ts):
+            if i == na:
+                o = self.cri_off
+            if i == len(ts) - 1:
+                o = self.astd_off
+            out.append((t, o))
+            o += t.numel()
+        return out
+
     def load(self, act, cri):
         with torch.no_grad():
-            torch.cat([t.detach().reshape(-1) for t in self._tensors(act, cri)], out=self.theta)
+            for t, o in self._slices(act, cri):
+                self.theta[o:o + t.numel()].copy_(t.detach().reshape(-1))
         self.L.check(self.L.lib().pime_ppo_transpose(self.C.byref(self.cfg), self.L.ptr(self.theta), self.L.ptr(self.theta_t),
                                                      self.L.stream_ptr()))
 
     def store(self, act, cri):
         with torch.no_grad():
-            o = 0
-            for t in self._tensors(act, cri):
+            for t, o in self._slices(act, cri):
                 t.copy_(self.theta[o:o + t.numel()].view_as(t))
-                o += t.numel()
 
     def step(self, data, idx, agent, grad_out=None):
         """One minibatch step on rows ``idx`` of data = (state, action, r_sum, logprob, advantage)."""

@@ -254,12 +254,8 @@ def _fused_setup(g, tag, lr=3e-4):
 
 
 def _split(f, agent, flat):
-    out, o = {}, 0
     names = [k for k in f._keys[0]] + ["cri." + k for k in f._keys[1]] + ["a_std_log"]
-    for name, t in zip(names, f._tensors(agent.act, agent.cri)):
-        out[name] = flat[o:o + t.numel()].view_as(t).cpu().numpy()
-        o += t.numel()
-    return out
+    return {name: flat[o:o + t.numel()].view_as(t).cpu().numpy() for name, (t, o) in zip(names, f._slices(agent.act, agent.cri))}
 
 
 @pytest.mark.parametrize("tag", ["modular", "plain"])
@@ -287,16 +283,12 @@ def test_fused_ppo_kernels_match_the_reference_gradients_and_adam_step(golden, t
                 np.testing.assert_allclose(net.state_dict()[k[len(pre):]].cpu().numpy(), g[k], rtol=1e-5, atol=1e-6, err_msg=k)
     # the transposed copy the forward pass reads follows the update
     w = agent.cri.net[2].weight
-    o = sum(t.numel() for t in f._tensors(agent.act, agent.cri)[:len(f._keys[0]) + 2])
+    o = dict((id(t), o) for t, o in f._slices(agent.act, agent.cri))[id(w)]
     assert torch.equal(f.theta_t[o:o + w.numel()].view(w.shape[1], w.shape[0]).t(), w)
 
 
 def _split_t(f, agent, flat):
-    o, out = 0, []
-    for t in f._tensors(agent.act, agent.cri):
-        out.append(flat[o:o + t.numel()].view_as(t))
-        o += t.numel()
-    return out
+    return [flat[o:o + t.numel()].view_as(t) for t, o in f._slices(agent.act, agent.cri)]
 
 
 @pytest.mark.parametrize("kind,S,H,B", [("modular", 4, 256, 256), ("modular", 3, 128, 128), ("plain", 30, 256, 200),
