@@ -449,6 +449,11 @@ __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, bool
     const int bytes = valid ? 16 : 0;   // 0: the 16 bytes are zero-filled, nothing is read
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    const int bytes = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -488,14 +493,16 @@ __global__ void __launch_bounds__(kThreads) ppo_wgrad_kernel(const StepParams p)
                 const bool ok = b < B && k0 + c + 4 <= in_avail;
                 cp_async16(&sI[stage][r][c], ok ? in + (size_t)b * in_stride + k0 + c : in, ok);
             }
-        } else {
+        } else {   // element-wise asynchronous copies (only the columns that exist are touched; the rest is zero-filled)
             for (int j = tid; j < kBk * kTileN; j += kThreads) {
                 const int r = j / kTileN, c = j % kTileN, b = bb + r;
-                sD[stage][r][c] = (b < B && n0 + c < L.N) ? dz[(size_t)b * dz_stride + n0 + c] : 0.0f;
+                const bool ok = b < B && n0 + c < L.N;
+                cp_async4(&sD[stage][r][c], ok ? dz + (size_t)b * dz_stride + n0 + c : dz, ok);
             }
             for (int j = tid; j < kBk * kTileK; j += kThreads) {
                 const int r = j / kTileK, c = j % kTileK, b = bb + r;
-                sI[stage][r][c] = (b < B && k0 + c < L.K) ? in[(size_t)b * in_stride + k0 + c] : 0.0f;
+                const bool ok = b < B && k0 + c < L.K;
+                cp_async4(&sI[stage][r][c], ok ? in + (size_t)b * in_stride + k0 + c : in, ok);
             }
         }
         cp_async_commit();
@@ -733,7 +740,7 @@ int pime_ppo_step(const pime_ppo_args *a, void *stream) {
     p.DZ_C = w; w += B * p.cri.LA;
     p.DOUT = w;
     cudaStream_t s = (cudaStream_t)stream;
-    const int R = B <= 128 ? 2 : (B <= 256 ? 4 : 8);   // ~64 CTAs at the reference's batch sizes; weights stream once per CTA
+    const int R = B <= 256 ? 2 : (B <= 512 ? 4 : 8);   // 64-128 CTAs at the reference's batch sizes; weights stream once per CTA
     int rc = R == 2 ? ppo::launch_rows<2>(p, s) : (R == 4 ? ppo::launch_rows<4>(p, s) : ppo::launch_rows<8>(p, s));
     if (rc) return rc;
     ppo::ppo_wgrad_kernel<<<p.n_tiles, ppo::kThreads, 0, s>>>(p);

@@ -227,6 +227,8 @@ class FusedLearner:
         self.loss_ring = torch.zeros((self.RING, 4), dtype=torch.float32, device=device)
         self.work = None
         self.steps = 0          # host mirror of the device step count
+        self._args = None
+        self._step_fn = V.L.lib().pime_ppo_step
         self._keys = (V.ActorPack.KEYS[act.kind], V.ActorPack.KEYS["critic"])
 
     @staticmethod
@@ -270,19 +272,24 @@ class FusedLearner:
     def step(self, data, idx, agent, grad_out=None):
         """One minibatch step on rows ``idx`` of data = (state, action, r_sum, logprob, advantage)."""
         C, L = self.C, self.L
-        state, action, r_sum, logprob, advantage = data
         B = int(idx.numel())
-        need = int(L.lib().pime_ppo_work_floats(C.byref(self.cfg), C.c_int32(B)))
-        if self.work is None or self.work.numel() < need:
-            self.work = torch.empty(need, dtype=torch.float32, device=self.device)
-        grp = agent.optimizer.param_groups[0]
-        a = L.PpoArgs(actor=C.pointer(self.cfg), theta=L.ptr(self.theta), theta_t=L.ptr(self.theta_t), adam_m=L.ptr(self.m),
-                      adam_v=L.ptr(self.v), grad_out=L.ptr(grad_out), buf_state=L.ptr(state), buf_action=L.ptr(action),
-                      buf_r_sum=L.ptr(r_sum), buf_logprob=L.ptr(logprob), buf_advantage=L.ptr(advantage), idx=L.ptr(idx),
-                      batch=B, ratio_clip=agent.ratio_clip, lambda_entropy=agent.lambda_entropy, lr=grp["lr"],
-                      beta1=grp["betas"][0], beta2=grp["betas"][1], eps=grp["eps"], state=L.ptr(self.state),
-                      work=L.ptr(self.work), loss_ring=L.ptr(self.loss_ring), ring_len=self.RING)
-        L.check(L.lib().pime_ppo_step(C.byref(a), L.stream_ptr()))
+        key = (tuple(t.data_ptr() for t in data), B, None if grad_out is None else grad_out.data_ptr())
+        if self._args is None or self._args[0] != key:      # the argument block is rebuilt only when a pointer changes
+            state, action, r_sum, logprob, advantage = data
+            need = int(L.lib().pime_ppo_work_floats(C.byref(self.cfg), C.c_int32(B)))
+            if self.work is None or self.work.numel() < need:
+                self.work = torch.empty(need, dtype=torch.float32, device=self.device)
+            grp = agent.optimizer.param_groups[0]
+            a = L.PpoArgs(actor=C.pointer(self.cfg), theta=L.ptr(self.theta), theta_t=L.ptr(self.theta_t), adam_m=L.ptr(self.m),
+                          adam_v=L.ptr(self.v), grad_out=L.ptr(grad_out), buf_state=L.ptr(state), buf_action=L.ptr(action),
+                          buf_r_sum=L.ptr(r_sum), buf_logprob=L.ptr(logprob), buf_advantage=L.ptr(advantage), batch=B,
+                          ratio_clip=agent.ratio_clip, lambda_entropy=agent.lambda_entropy, lr=grp["lr"],
+                          beta1=grp["betas"][0], beta2=grp["betas"][1], eps=grp["eps"], state=L.ptr(self.state),
+                          work=L.ptr(self.work), loss_ring=L.ptr(self.loss_ring), ring_len=self.RING)
+            self._args = (key, a, C.byref(a), data)
+        a = self._args[1]
+        a.idx = idx.data_ptr()
+        L.check(self._step_fn(self._args[2], C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         self.steps += 1
 
     def losses(self, first, count):
@@ -608,6 +615,7 @@ class AgentPPO:
             idx = torch.randint(buf_len, size=(batch_size,), device=self.device)
             f.step(data, idx, self)
         f.store(self.act, self.cri)
+        f._args = None                      # do not keep the replay tensors alive between calls
         self._n_updates += int(repeat_times)
         keep = min(iters, f.RING - 1)
         rows = f.losses(first + iters - keep, keep)
