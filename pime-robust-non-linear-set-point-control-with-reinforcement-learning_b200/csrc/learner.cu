@@ -30,6 +30,7 @@ constexpr int kXStride = 32;      // gathered state row (S <= 32)
 constexpr int kRowVals = 8;       // per-row scalars in shared memory
 constexpr int kTileN = 32, kTileK = 64;   // weight-gradient tile
 constexpr int kBk = 32;           // minibatch rows per shared-memory stage of the weight-gradient kernel
+constexpr int kWgStages = 2;
 
 enum { ACT_NONE = 0, ACT_TANH = 1, ACT_RELU = 2 };
 
@@ -112,6 +113,9 @@ __device__ __forceinline__ void fwd_layer(const float *in, int in_stride, int K,
     }
 }
 
+// barrier of the 8 compute warps of the rows kernel (the streaming warp never joins)
+__device__ __forceinline__ void sync_compute() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
+
 // The weight ring: warp 8 streams every hidden-layer matrix of the step, slab by slab (cp.async.bulk, kStages in flight,
 // so the L2 latency is paid once); the 8 compute warps consume the slabs in the same order.
 struct Ring {
@@ -129,9 +133,96 @@ struct Ring {
     }
 };
 
-// hidden layer forward through the ring: out[r][n] = act(b[n] + sum_k in[r][k] Wt[k][n]), thread n
+// One streamed matrix [ROWS][COLS] against R operand rows x[r][0..ROWS): part[g][r][c] = sum over the slab rows of group g
+// of x[r][row] * W[row][c].  Thread = (4 adjacent columns) x (one of G = 1024 / COLS row groups): a float4 of weights and a
+// few operand values per 4*R..16*R FMAs, instead of one shared-memory load per R FMAs with a thread per column.  The
+// caller sums the G partials.  COLS in {64, 128, 256}.
+template <int R, int COLS>
+__device__ __forceinline__ void ring_gemm(Ring &ring, const float *x, int xs, int ROWS, float *part) {
+    constexpr int CG = COLS / 4, G = kThreads / CG, RPG = kSlabRows / G;   // 256: G=4, 4 rows per group and slab; 128: 8, 2; 64: 16, 1
+    const int cg = threadIdx.x % CG, g = threadIdx.x / CG;
+    float acc[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+    for (int r0 = 0; r0 < ROWS; r0 += kSlabRows) {
+        const float *w = ring.acquire() + (g * RPG) * COLS + cg * 4;
+        float4 wv[RPG];
+#pragma unroll
+        for (int i = 0; i < RPG; ++i) wv[i] = *reinterpret_cast<const float4 *>(w + i * COLS);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float xv[RPG];
+            const float *xp = x + r * xs + r0 + g * RPG;
+            if constexpr (RPG == 4) { const float4 t = *reinterpret_cast<const float4 *>(xp); xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w; }
+            else if constexpr (RPG == 2) { const float2 t = *reinterpret_cast<const float2 *>(xp); xv[0] = t.x; xv[1] = t.y; }
+            else xv[0] = xp[0];
+#pragma unroll
+            for (int i = 0; i < RPG; ++i) {
+                acc[r][0] = fmaf(xv[i], wv[i].x, acc[r][0]); acc[r][1] = fmaf(xv[i], wv[i].y, acc[r][1]);
+                acc[r][2] = fmaf(xv[i], wv[i].z, acc[r][2]); acc[r][3] = fmaf(xv[i], wv[i].w, acc[r][3]);
+            }
+        }
+        ring.release();
+    }
+    sync_compute();   // every thread has left the previous layer's reduction, which reads part
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        *reinterpret_cast<float4 *>(part + (g * R + r) * COLS + cg * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    sync_compute();
+}
+template <int R, int COLS> __device__ __forceinline__ float part_sum(const float *part, int r, int c) {
+    constexpr int G = kThreads / (COLS / 4);
+    float s = 0.0f;
+#pragma unroll
+    for (int g = 0; g < G; ++g) s += part[(g * R + r) * COLS + c];
+    return s;
+}
+
+template <int R> __device__ __forceinline__ void fwd_ring_narrow(Ring &ring, const float *in, int in_stride, int K, const float *__restrict__ bias,
+                                                                 int N, int act, float *out, int out_stride);
+template <int R> __device__ __forceinline__ void bwd_ring_narrow(Ring &ring, const float *dz_out, int dzo_stride, int N, int K, const float *a_in,
+                                                                 int a_stride, int act_in, float *dz_in, int dzi_stride);
+
+// hidden layer forward through the ring: out[r][n] = act(b[n] + sum_k in[r][k] Wt[k][n])
 template <int R>
 __device__ __forceinline__ void fwd_ring(Ring &ring, const float *in, int in_stride, int K, const float *__restrict__ bias, int N, int act,
+                                         float *out, int out_stride, float *part) {
+    if (N == 256) ring_gemm<R, 256>(ring, in, in_stride, K, part);
+    else if (N == 128) ring_gemm<R, 128>(ring, in, in_stride, K, part);
+    else if (N == 64) ring_gemm<R, 64>(ring, in, in_stride, K, part);
+    else { fwd_ring_narrow<R>(ring, in, in_stride, K, bias, N, act, out, out_stride); return; }
+    const int n = threadIdx.x;
+    if (n < N) {
+        const float b = __ldg(bias + n);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float s = N == 256 ? part_sum<R, 256>(part, r, n) : (N == 128 ? part_sum<R, 128>(part, r, n) : part_sum<R, 64>(part, r, n));
+            out[r * out_stride + n] = act_apply(act, b + s);
+        }
+    }
+}
+
+// hidden layer backward through the ring: dz_in[r][k] = act'(a_in[r][k]) * sum_n dz_out[r][n] W[n][k]
+template <int R>
+__device__ __forceinline__ void bwd_ring(Ring &ring, const float *dz_out, int dzo_stride, int N, int K, const float *a_in, int a_stride,
+                                         int act_in, float *dz_in, int dzi_stride, float *part) {
+    if (K == 256) ring_gemm<R, 256>(ring, dz_out, dzo_stride, N, part);
+    else if (K == 128) ring_gemm<R, 128>(ring, dz_out, dzo_stride, N, part);
+    else if (K == 64) ring_gemm<R, 64>(ring, dz_out, dzo_stride, N, part);
+    else { bwd_ring_narrow<R>(ring, dz_out, dzo_stride, N, K, a_in, a_stride, act_in, dz_in, dzi_stride); return; }
+    const int k = threadIdx.x;
+    if (k < K) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float s = K == 256 ? part_sum<R, 256>(part, r, k) : (K == 128 ? part_sum<R, 128>(part, r, k) : part_sum<R, 64>(part, r, k));
+            dz_in[r * dzi_stride + k] = s * act_grad(act_in, a_in[r * a_stride + k]);
+        }
+    }
+}
+
+// narrow layers (fewer than 64 columns): a thread per column
+template <int R>
+__device__ __forceinline__ void fwd_ring_narrow(Ring &ring, const float *in, int in_stride, int K, const float *__restrict__ bias, int N, int act,
                                          float *out, int out_stride) {
     const int n = threadIdx.x;
     const bool on = n < N;
@@ -163,8 +254,8 @@ __device__ __forceinline__ void fwd_ring(Ring &ring, const float *in, int in_str
 
 // hidden layer backward through the ring: dz_in[r][k] = act'(a_in[r][k]) * sum_n dz_out[r][n] W[n][k], thread k (K == kThreads or less)
 template <int R>
-__device__ __forceinline__ void bwd_ring(Ring &ring, const float *dz_out, int dzo_stride, int N, int K, const float *a_in, int a_stride,
-                                         int act_in, float *dz_in, int dzi_stride) {
+__device__ __forceinline__ void bwd_ring_narrow(Ring &ring, const float *dz_out, int dzo_stride, int N, int K, const float *a_in, int a_stride,
+                                                int act_in, float *dz_in, int dzi_stride) {
     const int k = threadIdx.x;
     const bool on = k < K;
     float acc[R];
@@ -217,9 +308,6 @@ __device__ __forceinline__ void bwd_out(const float *d_out, int d_stride, const 
     }
 }
 
-// barrier of the 8 compute warps of the rows kernel (the streaming warp never joins)
-__device__ __forceinline__ void sync_compute() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
-
 __device__ __forceinline__ float block_sum(float v, float *scratch) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -237,26 +325,26 @@ __device__ __forceinline__ float block_sum(float v, float *scratch) {
 // hidden layers take their weights from the ring in the order fill_passes() lists them.
 template <int R>
 __device__ __forceinline__ void net_forward(Ring &ring, const NetDims &d, const float *__restrict__ th, const float *__restrict__ tt,
-                                            const float *sX, float *A, int as, float *out, int out_stride) {
+                                            const float *sX, float *A, int as, float *out, int out_stride, float *part) {
     const int H = d.H;
     if (d.kind == PIME_ACTOR_MODULAR) {   // net_residual.py:150-170
         const int Hh = H / 2;
         fwd_layer<R>(sX, kXStride, d.So, tt + d.src[0], th + d.src[1], H, ACT_TANH, A, as);                       // other_net.0
         fwd_layer<R>(sX + d.So, kXStride, d.S - d.So, tt + d.src[4], th + d.src[5], H, ACT_TANH, A + H, as);     // integrator_net.0
         sync_compute();
-        fwd_ring<R>(ring, A, as, H, th + d.src[3], Hh, ACT_TANH, A + 2 * H, as);                                  // other_net.2
-        fwd_ring<R>(ring, A + H, as, H, th + d.src[7], Hh, ACT_TANH, A + 2 * H + Hh, as);                         // integrator_net.2
+        fwd_ring<R>(ring, A, as, H, th + d.src[3], Hh, ACT_TANH, A + 2 * H, as, part);                                  // other_net.2
+        fwd_ring<R>(ring, A + H, as, H, th + d.src[7], Hh, ACT_TANH, A + 2 * H + Hh, as, part);                         // integrator_net.2
         sync_compute();
-        fwd_ring<R>(ring, A + 2 * H, as, H, th + d.src[9], H, ACT_TANH, A + 3 * H, as);                           // net.0 on cat
+        fwd_ring<R>(ring, A + 2 * H, as, H, th + d.src[9], H, ACT_TANH, A + 3 * H, as, part);                           // net.0 on cat
         sync_compute();
         fwd_out<R>(A + 3 * H, as, H, th + d.src[10], __ldg(th + d.src[11]), out, out_stride);                     // net.2
     } else {                               // plain actor (tanh) / CriticAdv (relu)
         const int act = d.kind == PIME_CRITIC_ADV ? ACT_RELU : ACT_TANH;
         fwd_layer<R>(sX, kXStride, d.S, tt + d.src[0], th + d.src[1], H, act, A, as);
         sync_compute();
-        fwd_ring<R>(ring, A, as, H, th + d.src[3], H, act, A + H, as);
+        fwd_ring<R>(ring, A, as, H, th + d.src[3], H, act, A + H, as, part);
         sync_compute();
-        fwd_ring<R>(ring, A + H, as, H, th + d.src[5], H, act, A + 2 * H, as);
+        fwd_ring<R>(ring, A + H, as, H, th + d.src[5], H, act, A + 2 * H, as, part);
         sync_compute();
         fwd_out<R>(A + 2 * H, as, H, th + d.src[6], __ldg(th + d.src[7]), out, out_stride);
     }
@@ -265,23 +353,23 @@ __device__ __forceinline__ void net_forward(Ring &ring, const NetDims &d, const 
 
 template <int R>
 __device__ __forceinline__ void net_backward(Ring &ring, const NetDims &d, const float *__restrict__ th, const float *A, float *Z, int as,
-                                             const float *d_out, int d_stride) {
+                                             const float *d_out, int d_stride, float *part) {
     const int H = d.H;
     if (d.kind == PIME_ACTOR_MODULAR) {
         const int Hh = H / 2;
         bwd_out<R>(d_out, d_stride, th + d.src[10], H, A + 3 * H, as, ACT_TANH, Z + 3 * H, as);                   // -> dZ(net.0)
         sync_compute();
-        bwd_ring<R>(ring, Z + 3 * H, as, H, H, A + 2 * H, as, ACT_TANH, Z + 2 * H, as);                           // net.0 -> dZ(other_net.2 | integrator_net.2)
+        bwd_ring<R>(ring, Z + 3 * H, as, H, H, A + 2 * H, as, ACT_TANH, Z + 2 * H, as, part);                           // net.0 -> dZ(other_net.2 | integrator_net.2)
         sync_compute();
-        bwd_ring<R>(ring, Z + 2 * H, as, Hh, H, A, as, ACT_TANH, Z, as);                                          // other_net.2 -> dZ(other_net.0)
-        bwd_ring<R>(ring, Z + 2 * H + Hh, as, Hh, H, A + H, as, ACT_TANH, Z + H, as);                             // integrator_net.2 -> dZ(integrator_net.0)
+        bwd_ring<R>(ring, Z + 2 * H, as, Hh, H, A, as, ACT_TANH, Z, as, part);                                          // other_net.2 -> dZ(other_net.0)
+        bwd_ring<R>(ring, Z + 2 * H + Hh, as, Hh, H, A + H, as, ACT_TANH, Z + H, as, part);                             // integrator_net.2 -> dZ(integrator_net.0)
     } else {
         const int act = d.kind == PIME_CRITIC_ADV ? ACT_RELU : ACT_TANH;
         bwd_out<R>(d_out, d_stride, th + d.src[6], H, A + 2 * H, as, act, Z + 2 * H, as);
         sync_compute();
-        bwd_ring<R>(ring, Z + 2 * H, as, H, H, A + H, as, act, Z + H, as);                                        // net.4
+        bwd_ring<R>(ring, Z + 2 * H, as, H, H, A + H, as, act, Z + H, as, part);                                        // net.4
         sync_compute();
-        bwd_ring<R>(ring, Z + H, as, H, H, A, as, act, Z, as);                                                    // net.2
+        bwd_ring<R>(ring, Z + H, as, H, H, A, as, act, Z, as, part);                                                    // net.2
     }
     sync_compute();
 }
@@ -322,6 +410,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) ppo_rows_kernel(const StepPar
     float *sZ = sA + R * LA;                // [R][LA] pre-activation gradients
     float *sV = sZ + R * LA;                // [R][kRowVals]: action, r_sum, logprob_old, advantage, a_avg, value, d_a, d_v
     float *sRed = sV + R * kRowVals;        // [8]
+    float *sPart = sRed + 8;                // [1024 / COLS * ... ] = 1024 R floats: partial sums of ring_gemm
     const int tid = threadIdx.x;
     const int B = p.B;
     const int b0 = blockIdx.x * R;
@@ -358,8 +447,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) ppo_rows_kernel(const StepPar
 
     const float *thA = p.theta + p.act.theta_off, *ttA = p.theta_t + p.act.theta_off;
     const float *thC = p.theta + p.cri.theta_off, *ttC = p.theta_t + p.cri.theta_off;
-    net_forward<R>(ring, p.act, thA, ttA, sX, sA, LA, sV + 4, kRowVals);
-    net_forward<R>(ring, p.cri, thC, ttC, sX, sA + LAa, LA, sV + 5, kRowVals);
+    net_forward<R>(ring, p.act, thA, ttA, sX, sA, LA, sV + 4, kRowVals, sPart);
+    net_forward<R>(ring, p.cri, thC, ttC, sX, sA + LAa, LA, sV + 5, kRowVals, sPart);
 
     // objectives and their gradients (agent.py:635-652), one thread per row
     if (tid < R) {
@@ -405,8 +494,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) ppo_rows_kernel(const StepPar
     }
     sync_compute();
 
-    net_backward<R>(ring, p.act, thA, sA, sZ, LA, sV + 6, kRowVals);
-    net_backward<R>(ring, p.cri, thC, sA + LAa, sZ + LAa, LA, sV + 7, kRowVals);
+    net_backward<R>(ring, p.act, thA, sA, sZ, LA, sV + 6, kRowVals, sPart);
+    net_backward<R>(ring, p.cri, thC, sA + LAa, sZ + LAa, LA, sV + 7, kRowVals, sPart);
 
     // rows -> scratch (inputs of the weight-gradient kernel)
     for (int r = 0; r < R; ++r) {
@@ -458,8 +547,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(kThreads) ppo_wgrad_kernel(const StepParams p) {
-    __shared__ __align__(16) float sD[2][kBk][kTileN + 4];   // dZ[b][n0 + .], two stages
-    __shared__ __align__(16) float sI[2][kBk][kTileK + 4];   // input[b][k0 + .]
+    __shared__ __align__(16) float sD[kWgStages][kBk][kTileN + 4];   // dZ[b][n0 + .], kWgStages stages in flight
+    __shared__ __align__(16) float sI[kWgStages][kBk][kTileK + 4];   // input[b][k0 + .]
     __shared__ bool is_last;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;   // tx: 4 columns of k, ty: 2 rows of n
     int li = 0;
@@ -516,11 +605,13 @@ __global__ void __launch_bounds__(kThreads) ppo_wgrad_kernel(const StepParams p)
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
     }
     const int nst = (B + kBk - 1) / kBk;
-    fill(0, 0);
+    for (int j = 0; j < kWgStages - 1; ++j) {   // one commit group per stage, empty groups past the end keep the count uniform
+        if (j < nst) fill(j, j * kBk); else cp_async_commit();
+    }
     for (int it = 0; it < nst; ++it) {
-        const int cur = it & 1;
-        if (it + 1 < nst) { fill(cur ^ 1, (it + 1) * kBk); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
+        const int cur = it % kWgStages;
+        if (it + kWgStages - 1 < nst) fill((it + kWgStages - 1) % kWgStages, (it + kWgStages - 1) * kBk); else cp_async_commit();
+        cp_async_wait<kWgStages - 1>();
         __syncthreads();
 #pragma unroll 8
         for (int r = 0; r < kBk; ++r) {
@@ -664,7 +755,7 @@ static int fill_params(const pime_ppo_args *a, StepParams &p) {
 static int64_t work_floats_per_row(const StepParams &p) { return kXStride + 2 * (int64_t)(p.act.LA + p.cri.LA) + 2; }
 
 template <int R> static int launch_rows(const StepParams &p, cudaStream_t s) {
-    const size_t smem = sizeof(float) * (size_t)(kStages * kSlabFloats + R * (kXStride + 2 * (p.act.LA + p.cri.LA) + kRowVals) + 8) +
+    const size_t smem = sizeof(float) * (size_t)(kStages * kSlabFloats + R * (kXStride + 2 * (p.act.LA + p.cri.LA) + kRowVals) + 8 + 1024 * R) +
                         2 * kStages * sizeof(uint64_t);
     auto kern = ppo_rows_kernel<R>;
     PIME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
