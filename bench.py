@@ -438,8 +438,10 @@ def aux_step_rooflines(V, pk):
 
 
 def run_train(args):
-    """configs[4]: explore (one fused launch) -> update_net (values + GAE kernels, torch-autograd minibatches, flat grad
-    all-reduce) per step; reports transitions/s end to end and the rollout share.  Not the bench line."""
+    """configs[4]: explore (one fused launch) -> update_net (values + GAE kernels; minibatch step: pime_ppo_step up to
+    4096 rows, torch autograd above; flat grad all-reduce when distributed) per step; reports transitions/s end to end
+    and the rollout share.  Not the bench line.  The reference's own shape (run_watertank_changing.sh: target_step 2000,
+    batch 256, repeat 10): --envs 10 --batch-size 256 --repeat-times 10."""
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -494,8 +496,9 @@ def run_train(args):
                           "config": {"workload": w["name"], "envs_per_gpu": n, "T": T, "actor": w["actor"], "batch_size": args.batch_size,
                                      "repeat_times": args.repeat_times,
                                      "minibatches_per_step": int(args.repeat_times * n * T / args.batch_size),
-                                     "learner": "values + GAE: CUDA kernels; minibatch step: torch autograd (cuBLAS, "
-                                                + ("TF32" if args.tf32 else "fp32") + ")"},
+                                     "learner": "values + GAE: CUDA kernels; minibatch step: "
+                                                + ("pime_ppo_step (two hand-written launches, fp32, fused Adam)" if agent._fused is not None
+                                                   else "torch autograd (cuBLAS, " + ("TF32" if args.tf32 else "fp32") + ")")},
                           "rollout_share": t_roll / (t_roll + t_upd), "rollout_ms_per_step": 1e3 * t_roll / args.steps,
                           "update_ms_per_step": 1e3 * t_upd / args.steps}), flush=True)
     if world > 1:
