@@ -422,6 +422,7 @@ class AgentPPO:
                                            {"params": self.cri.parameters(), "lr": self.learning_rate}],
                                           capturable=on_gpu, fused=True if on_gpu else None)   # one Adam kernel per step
         self._graph = None
+        self._fused = None      # a new optimizer starts from zero moments on the fused path too
 
     def init_actor_zero(self):
         """agent_residual.py:45-50: last layer zeroed -> the policy starts exactly at the prior."""
