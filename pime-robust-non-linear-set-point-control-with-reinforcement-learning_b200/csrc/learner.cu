@@ -23,7 +23,7 @@ constexpr int kThreads = 256;          // compute threads of the rows kernel (on
 constexpr int kRowsThreads = kThreads + 32;
 constexpr int kSlabRows = 16;          // weight rows per streamed slab
 constexpr int kSlabFloats = kSlabRows * 256;
-constexpr int kStages = 4;             // slabs in flight (cp.async.bulk ring)
+constexpr int kMaxStages = 8;          // slabs in flight (cp.async.bulk ring): 8 (128 KB) up to 4 rows per CTA, 4 at 8 rows
 constexpr int kMaxPasses = 12;
 constexpr int kMaxLayers = 10;
 constexpr int kXStride = 32;      // gathered state row (S <= 32)
@@ -121,7 +121,7 @@ __device__ __forceinline__ void sync_compute() { asm volatile("bar.sync 1, %0;" 
 struct Ring {
     float *buf;
     uint64_t *full, *empty;
-    uint32_t st, ph;
+    uint32_t st, ph, nst;
     __device__ __forceinline__ const float *acquire() {
         tc::mbar_wait(&full[st], ph);
         return buf + st * kSlabFloats;
@@ -129,7 +129,7 @@ struct Ring {
     __device__ __forceinline__ void release() {
         __syncwarp();
         if ((threadIdx.x & 31) == 0) tc::mbar_arrive(&empty[st]);
-        if (++st == kStages) { st = 0; ph ^= 1; }
+        if (++st == nst) { st = 0; ph ^= 1; }
     }
 };
 
@@ -379,10 +379,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1) ppo_rows_kernel(const StepPar
     extern __shared__ __align__(128) float sm[];
     const int LAa = p.act.LA, LAc = p.cri.LA, LA = LAa + LAc;
     Ring ring;
+    constexpr int kStages = R <= 4 ? kMaxStages : 4;
     ring.buf = sm;                          // [kStages][kSlabFloats]
     ring.full = reinterpret_cast<uint64_t *>(sm + kStages * kSlabFloats);
     ring.empty = ring.full + kStages;
-    ring.st = 0; ring.ph = 0;
+    ring.st = 0; ring.ph = 0; ring.nst = kStages;
     if (threadIdx.x == 0) {
         for (int j = 0; j < kStages; ++j) { tc::mbar_init(&ring.full[j], 1); tc::mbar_init(&ring.empty[j], kThreads / 32); }
         tc::fence_barrier_init();
@@ -755,6 +756,7 @@ static int fill_params(const pime_ppo_args *a, StepParams &p) {
 static int64_t work_floats_per_row(const StepParams &p) { return kXStride + 2 * (int64_t)(p.act.LA + p.cri.LA) + 2; }
 
 template <int R> static int launch_rows(const StepParams &p, cudaStream_t s) {
+    constexpr int kStages = R <= 4 ? kMaxStages : 4;
     const size_t smem = sizeof(float) * (size_t)(kStages * kSlabFloats + R * (kXStride + 2 * (p.act.LA + p.cri.LA) + kRowVals) + 8 + 1024 * R) +
                         2 * kStages * sizeof(uint64_t);
     auto kern = ppo_rows_kernel<R>;
