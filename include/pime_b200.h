@@ -293,8 +293,8 @@ int pime_wt_rollout_host_f32(const pime_wt_config *cfg, int64_t n, const pime_wt
  * theta = [actor parameters | pad | critic parameters | a_std_log], each net in state_dict order (pime_actor_param_count
  * floats; the critic is CriticAdv with the actor's S and H; its offset, a multiple of 4 floats, the offset of
  * a_std_log and the total come from pime_ppo_theta_layout); theta_t holds every weight matrix transposed
- * (pime_ppo_transpose; kept up to date by the step).  state: device int32[4], zero-initialised, owned by the
- * library between steps (Adam step count, a ticket, the a_std_log gradient accumulator).  loss_ring: device
+ * (pime_ppo_transpose; kept up to date by the step).  state: device int32[1024], zero-initialised, owned by the
+ * library between steps (Adam step count, a ticket, the a_std_log and output-layer gradient accumulators).  loss_ring: device
  * float[ring_len][4], zero-initialised; step t (0-based count before the call) adds the means of (obj_united,
  * obj_actor, obj_critic, obj_entropy) to row t % ring_len and clears the next row.
  * ------------------------------------------------------------------------------------------------------- */

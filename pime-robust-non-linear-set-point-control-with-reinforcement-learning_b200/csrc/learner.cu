@@ -26,6 +26,8 @@ constexpr int kSlabFloats = kSlabRows * 256;
 constexpr int kMaxStages = 8;          // slabs in flight (cp.async.bulk ring): 8 (128 KB) up to 4 rows per CTA, 4 at 8 rows
 constexpr int kMaxPasses = 12;
 constexpr int kMaxLayers = 10;
+constexpr int kOutAcc = 272;           // floats per output-layer accumulator (H + 1 <= 257)
+constexpr int kXInt = 4;               // modular: aligned copy of the integrator observation inside the gathered row
 constexpr int kXStride = 32;      // gathered state row (S <= 32)
 constexpr int kRowVals = 8;       // per-row scalars in shared memory
 constexpr int kTileN = 32, kTileK = 64;   // weight-gradient tile
@@ -71,6 +73,7 @@ struct StepParams {
     int *step_dev;            // Adam step count so far (the step being taken is *step_dev + 1)
     unsigned *ticket;
     float *g_astd;            // accumulated gradient of a_std_log
+    float *g_out;             // [2][kOutAcc]: accumulated gradients of the two output layers Linear(H -> 1): weight[H], bias
     float *X, *ACT_A, *DZ_A, *ACT_C, *DZ_C, *DOUT;
     float *loss_ring;
     int ring_len;
@@ -433,6 +436,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) ppo_rows_kernel(const StepPar
         const int r = j / kXStride, c = j % kXStride, b = b0 + r;
         float x = 0.0f;
         if (b < B && c < p.act.S) x = __ldg(p.buf_state + __ldg(p.idx + b) * p.act.S + c);
+        else if (b < B && p.act.kind == PIME_ACTOR_MODULAR && c >= kXInt && c - kXInt < p.act.S - p.act.So)   // 16-byte aligned copy
+            x = __ldg(p.buf_state + __ldg(p.idx + b) * p.act.S + p.act.So + (c - kXInt));                      // for the weight-gradient kernel
         sX[j] = x;
     }
     if (tid < R) {
@@ -497,6 +502,16 @@ __global__ void __launch_bounds__(kRowsThreads, 1) ppo_rows_kernel(const StepPar
 
     net_backward<R>(ring, p.act, thA, sA, sZ, LA, sV + 6, kRowVals, sPart);
     net_backward<R>(ring, p.cri, thC, sA + LAa, sZ + LAa, LA, sV + 7, kRowVals, sPart);
+
+    // output layers Linear(H -> 1): weight / bias gradients of this CTA's rows, straight into the accumulators
+    for (int j = tid; j < 2 * (p.act.H + 1); j += kThreads) {
+        const int net = j / (p.act.H + 1), k = j % (p.act.H + 1);
+        const float *Alast = net == 0 ? sA + (p.act.kind == PIME_ACTOR_MODULAR ? 3 : 2) * p.act.H : sA + LAa + 2 * p.cri.H;
+        float g = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) g = fmaf(sV[r * kRowVals + 6 + net], k < p.act.H ? Alast[r * LA + k] : 1.0f, g);
+        atomicAdd(p.g_out + net * kOutAcc + k, g);
+    }
 
     // rows -> scratch (inputs of the weight-gradient kernel)
     for (int r = 0; r < R; ++r) {
@@ -654,15 +669,26 @@ __global__ void __launch_bounds__(kThreads) ppo_wgrad_kernel(const StepParams p)
     __syncthreads();
     if (tid == 0) is_last = atomicAdd(p.ticket, 1u) == (unsigned)p.n_tiles - 1u;
     __syncthreads();
-    if (is_last && tid == 0) {
+    if (is_last) {
         __threadfence();
-        const float g = *reinterpret_cast<volatile float *>(p.g_astd);
-        apply(p.n_theta - 1, p.n_theta - 1, g);
-        *p.g_astd = 0.0f;
-        *p.ticket = 0u;
-        float *nxt = p.loss_ring + (size_t)((*p.step_dev + 1) % p.ring_len) * 4;
-        nxt[0] = nxt[1] = nxt[2] = nxt[3] = 0.0f;
-        *p.step_dev = t;
+        for (int j = tid; j < 2 * (p.act.H + 1); j += kThreads) {   // the output layers, accumulated by the rows kernel
+            const int net = j / (p.act.H + 1), k = j % (p.act.H + 1);
+            const NetDims &d = net == 0 ? p.act : p.cri;
+            const int wi = d.kind == PIME_ACTOR_MODULAR ? 10 : 6;
+            const int idx = d.theta_off + (k < d.H ? d.src[wi] + k : d.src[wi + 1]);
+            float *acc_p = p.g_out + net * kOutAcc + k;
+            apply(idx, idx, *reinterpret_cast<volatile float *>(acc_p));
+            *acc_p = 0.0f;
+        }
+        if (tid == 0) {
+            const float g = *reinterpret_cast<volatile float *>(p.g_astd);
+            apply(p.n_theta - 1, p.n_theta - 1, g);
+            *p.g_astd = 0.0f;
+            *p.ticket = 0u;
+            float *nxt = p.loss_ring + (size_t)((*p.step_dev + 1) % p.ring_len) * 4;
+            nxt[0] = nxt[1] = nxt[2] = nxt[3] = 0.0f;
+            *p.step_dev = t;
+        }
     }
 }
 
@@ -694,7 +720,7 @@ static void add_layer(StepParams &p, int net, const NetDims &d, int N, int K, in
     LayerDesc &L = p.layer[p.n_layers++];
     L.net = net; L.N = N; L.K = K; L.w_off = d.theta_off + d.src[w]; L.b_off = d.theta_off + d.src[b];
     L.dz_col = dz_col; L.in_col = in_col; L.x_col = x_col;
-    L.tn = (N + kTileN - 1) / kTileN; L.tk = (K + kTileK - 1) / kTileK;
+    L.tn = N == 1 ? 0 : (N + kTileN - 1) / kTileN; L.tk = (K + kTileK - 1) / kTileK;   // Linear(H -> 1): see g_out
     L.tile0 = p.n_tiles;
     p.n_tiles += L.tn * L.tk;
 }
@@ -704,7 +730,7 @@ static void add_net_layers(StepParams &p, int net, const NetDims &d) {
     if (d.kind == PIME_ACTOR_MODULAR) {
         add_layer(p, net, d, H, d.So, 0, 1, 0, -1, 0);                      // other_net.0
         add_layer(p, net, d, H / 2, H, 2, 3, 2 * H, 0, 0);                  // other_net.2
-        add_layer(p, net, d, H, d.S - d.So, 4, 5, H, -1, d.So);             // integrator_net.0
+        add_layer(p, net, d, H, d.S - d.So, 4, 5, H, -1, kXInt);            // integrator_net.0 (aligned copy of its input)
         add_layer(p, net, d, H / 2, H, 6, 7, 2 * H + H / 2, H, 0);          // integrator_net.2
         add_layer(p, net, d, H, H, 8, 9, 3 * H, 2 * H, 0);                  // net.0
         add_layer(p, net, d, 1, H, 10, 11, -1, 3 * H, 0);                   // net.2
@@ -823,6 +849,7 @@ int pime_ppo_step(const pime_ppo_args *a, void *stream) {
     p.ratio_clip = a->ratio_clip; p.lambda_entropy = a->lambda_entropy;
     p.lr = a->lr; p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps;
     p.step_dev = (int *)a->state; p.ticket = (unsigned *)a->state + 1; p.g_astd = (float *)a->state + 2;
+    p.g_out = (float *)a->state + 16;
     p.loss_ring = a->loss_ring; p.ring_len = a->ring_len;
     const int64_t B = a->batch;
     float *w = a->work;

@@ -223,7 +223,7 @@ class FusedLearner:
         self.cri_off, self.astd_off, n = int(lay[0]), int(lay[1]), int(lay[2])
         self.device = device
         self.theta, self.theta_t, self.m, self.v = (torch.zeros(n, dtype=torch.float32, device=device) for _ in range(4))
-        self.state = torch.zeros(4, dtype=torch.int32, device=device)
+        self.state = torch.zeros(1024, dtype=torch.int32, device=device)
         self.loss_ring = torch.zeros((self.RING, 4), dtype=torch.float32, device=device)
         self.work = None
         self.steps = 0          # host mirror of the device step count
