@@ -364,3 +364,36 @@ def test_update_net_takes_the_fused_path_and_matches_autograd():
         for k in d1:
             assert float((d1[k] - d2[k]).abs().max()) <= 3 * lr, k        # 200 Adam steps of 1e-4 each: the same trajectory
             assert float((d1[k] - d2[k]).abs().mean()) <= 0.05 * lr, k
+
+
+def test_fused_learner_eligibility_and_plain_ppo_arm():
+    """The frozen_* variants keep the autograd step (their frozen tensors must not move); the plain PPO baseline arm
+    (agent.py:591-609, no prior) trains through the fused kernels like the residual agents."""
+    import pime_b200.rl as R
+    n = 64
+    env = _make(WT, n)
+    frozen = R.AgentResidualIntegratorModularPPO()
+    frozen.init(32, env.state_dim, env.action_dim, env.n_integrator)
+    frozen.init_residual({"init_K": env.K.reshape(-1, 1)})
+    frozen.frozen_integrator()
+    assert not R.FusedLearner.eligible(frozen, 256)
+    buf = R.ReplayBuffer(n * env.max_step, env.state_dim, 1, True, False, True, num_envs=n)
+    steps = frozen.explore_env(env, buf, n * env.max_step, 1.0, 0.99)
+    held = {k: v.clone() for k, v in frozen.act.state_dict().items() if k.startswith("integrator_net")}
+    frozen.update_net(buf, steps, 256, 1)
+    assert frozen._fused is None and all(torch.equal(frozen.act.state_dict()[k], v) for k, v in held.items())
+
+    plain = R.AgentPPO()
+    plain.init(32, env.state_dim, env.action_dim)
+    assert R.FusedLearner.eligible(plain, 256) and not R.FusedLearner.eligible(plain, 1 << 20)
+    buf2 = R.ReplayBuffer(n * env.max_step, env.state_dim, 1, True, False, True, num_envs=n)
+    steps = plain.explore_env(env, buf2, n * env.max_step, 1.0, 0.99)
+    before = {k: v.clone() for k, v in plain.act.state_dict().items()}
+    plain.update_net(buf2, steps, 256, 1)
+    plain.update_net(buf2, steps, 256, 4)
+    assert plain._fused is not None and plain._fused.steps == 5 * (steps // 256)
+    assert all(np.isfinite(R.logger.values[k]) for k in ("train/critic_loss", "train/actor_loss", "train/entropy_losses"))
+    assert all(torch.isfinite(v).all() for v in plain.act.state_dict().values())
+    assert any(not torch.equal(before[k], v) for k, v in plain.act.state_dict().items())
+    plain.init_actor_zero()                         # a new optimizer: the fused moments start over as well
+    assert plain._fused is None
