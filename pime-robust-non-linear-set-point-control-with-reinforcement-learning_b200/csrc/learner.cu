@@ -55,6 +55,7 @@ struct NetDims {
 struct StreamPass {       // one hidden-layer weight matrix streamed through the shared-memory ring, 16 rows per slab
     int off;              // offset in theta (backward: torch layout [N][K]) or theta_t (forward: [K][N])
     int transposed;       // 1: theta_t
+    int net;              // 0 actor, 1 critic
     int rows, cols;
 };
 
@@ -377,10 +378,15 @@ __device__ __forceinline__ void net_backward(Ring &ring, const NetDims &d, const
     sync_compute();
 }
 
+// grid = (row tiles, 2): blockIdx.y = 0 runs the actor (forward, policy objectives, backward), 1 the critic.  The two
+// nets share nothing but the gathered rows (obj_united = obj_actor + obj_critic / (std + 1e-5) is a sum), so splitting
+// them halves the chain of dependent layers a CTA walks through.
 template <int R>
 __global__ void __launch_bounds__(kRowsThreads, 1) ppo_rows_kernel(const StepParams p) {
     extern __shared__ __align__(128) float sm[];
-    const int LAa = p.act.LA, LAc = p.cri.LA, LA = LAa + LAc;
+    const int net = blockIdx.y;
+    const NetDims &d = net == 0 ? p.act : p.cri;
+    const int LA = d.LA;
     Ring ring;
     constexpr int kStages = R <= 4 ? kMaxStages : 4;
     ring.buf = sm;                          // [kStages][kSlabFloats]
@@ -392,11 +398,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) ppo_rows_kernel(const StepPar
         tc::fence_barrier_init();
     }
     __syncthreads();
-    if (threadIdx.x >= kThreads) {          // warp 8: streams every hidden-layer matrix of the step through the ring
+    if (threadIdx.x >= kThreads) {          // warp 8: streams every hidden-layer matrix of this net through the ring
         if (threadIdx.x == kThreads) {
             uint32_t st = 0, ph = 0;
             for (int q = 0; q < p.n_passes; ++q) {
                 const StreamPass P = p.pass[q];
+                if (P.net != net) continue;
                 const float *src = (P.transposed ? p.theta_t : p.theta) + P.off;
                 const uint32_t bytes = (uint32_t)(kSlabRows * P.cols * sizeof(float));
                 for (int r0 = 0; r0 < P.rows; r0 += kSlabRows) {
@@ -410,26 +417,28 @@ __global__ void __launch_bounds__(kRowsThreads, 1) ppo_rows_kernel(const StepPar
         return;
     }
     float *sX = reinterpret_cast<float *>(ring.empty + kStages);   // [R][kXStride]
-    float *sA = sX + R * kXStride;          // [R][LA] activations: actor | critic
+    float *sA = sX + R * kXStride;          // [R][LA] activations of this net
     float *sZ = sA + R * LA;                // [R][LA] pre-activation gradients
-    float *sV = sZ + R * LA;                // [R][kRowVals]: action, r_sum, logprob_old, advantage, a_avg, value, d_a, d_v
+    float *sV = sZ + R * LA;                // [R][kRowVals]: action, r_sum, logprob_old, advantage, net output, -, d output, -
     float *sRed = sV + R * kRowVals;        // [8]
-    float *sPart = sRed + 8;                // [1024 / COLS * ... ] = 1024 R floats: partial sums of ring_gemm
+    float *sPart = sRed + 8;                // 1024 R floats: partial sums of ring_gemm
     const int tid = threadIdx.x;
     const int B = p.B;
     const int b0 = blockIdx.x * R;
 
-    // r_sum.std() of the minibatch (agent.py:652; unbiased), two passes
-    float s = 0.0f;
-    for (int i = tid; i < B; i += kThreads) s += __ldg(p.buf_r_sum + __ldg(p.idx + i));
-    const float mean = block_sum(s, sRed) / (float)B;
-    s = 0.0f;
-    for (int i = tid; i < B; i += kThreads) {
-        const float dlt = __ldg(p.buf_r_sum + __ldg(p.idx + i)) - mean;
-        s = fmaf(dlt, dlt, s);
+    float inv_cs = 0.0f;
+    if (net == 1) {   // r_sum.std() of the minibatch (agent.py:652; unbiased), two passes
+        float s = 0.0f;
+        for (int i = tid; i < B; i += kThreads) s += __ldg(p.buf_r_sum + __ldg(p.idx + i));
+        const float mean = block_sum(s, sRed) / (float)B;
+        s = 0.0f;
+        for (int i = tid; i < B; i += kThreads) {
+            const float dlt = __ldg(p.buf_r_sum + __ldg(p.idx + i)) - mean;
+            s = fmaf(dlt, dlt, s);
+        }
+        const float rstd = sqrtf(block_sum(s, sRed) / (float)(B > 1 ? B - 1 : 1));
+        inv_cs = 1.0f / (rstd + 1e-5f);
     }
-    const float rstd = sqrtf(block_sum(s, sRed) / (float)(B > 1 ? B - 1 : 1));
-    const float inv_cs = 1.0f / (rstd + 1e-5f);
 
     // gather
     for (int j = tid; j < R * kXStride; j += kThreads) {
@@ -451,37 +460,39 @@ __global__ void __launch_bounds__(kRowsThreads, 1) ppo_rows_kernel(const StepPar
     }
     sync_compute();
 
-    const float *thA = p.theta + p.act.theta_off, *ttA = p.theta_t + p.act.theta_off;
-    const float *thC = p.theta + p.cri.theta_off, *ttC = p.theta_t + p.cri.theta_off;
-    net_forward<R>(ring, p.act, thA, ttA, sX, sA, LA, sV + 4, kRowVals, sPart);
-    net_forward<R>(ring, p.cri, thC, ttC, sX, sA + LAa, LA, sV + 5, kRowVals, sPart);
+    const float *th = p.theta + d.theta_off, *tt = p.theta_t + d.theta_off;
+    net_forward<R>(ring, d, th, tt, sX, sA, LA, sV + 4, kRowVals, sPart);
 
     // objectives and their gradients (agent.py:635-652), one thread per row
     if (tid < R) {
         float *rv = sV + tid * kRowVals;
         const bool live = b0 + tid < B;
         const float invB = 1.0f / (float)B;
-        const float asl = __ldg(p.theta + p.n_theta - 1);
-        const float std = expf(asl);
-        const float dd = (rv[4] - rv[0]) / std;
-        const float lp = -(asl + 0.9189385332046727f + dd * dd * 0.5f);      // compute_logprob (net_residual.py:62-66)
-        const float ratio = expf(lp - rv[2]);
-        const float adv = rv[3];
-        const float s1 = adv * ratio;
-        const float s2 = adv * fminf(fmaxf(ratio, 1.0f - p.ratio_clip), 1.0f + p.ratio_clip);
-        const float sur = fminf(s1, s2);
-        const float elp = expf(lp);
-        const float ent = elp * lp;
-        const float g_lp = (-(s1 <= s2 ? s1 : 0.0f) + p.lambda_entropy * (ent + elp)) * invB;   // d united / d new_logprob
-        const float e = rv[5] - rv[1];
-        const float ae = fabsf(e);
-        const float l1 = ae < 1.0f ? 0.5f * e * e : ae - 0.5f;                   // SmoothL1Loss, beta = 1
-        rv[6] = live ? g_lp * (-dd / std) : 0.0f;                                // d united / d a_avg
-        rv[7] = live ? fminf(fmaxf(e, -1.0f), 1.0f) * invB * inv_cs : 0.0f;      // d united / d value
-        float o_act = live ? (-sur + p.lambda_entropy * ent) * invB : 0.0f;
-        float o_cri = live ? l1 * invB : 0.0f;
-        float o_ent = live ? ent * invB : 0.0f;
-        float g_asl = live ? g_lp * (dd * dd - 1.0f) : 0.0f;
+        float o_act = 0.0f, o_cri = 0.0f, o_ent = 0.0f, g_asl = 0.0f;
+        if (net == 0) {
+            const float asl = __ldg(p.theta + p.n_theta - 1);
+            const float std = expf(asl);
+            const float dd = (rv[4] - rv[0]) / std;
+            const float lp = -(asl + 0.9189385332046727f + dd * dd * 0.5f);      // compute_logprob (net_residual.py:62-66)
+            const float ratio = expf(lp - rv[2]);
+            const float adv = rv[3];
+            const float s1 = adv * ratio;
+            const float s2 = adv * fminf(fmaxf(ratio, 1.0f - p.ratio_clip), 1.0f + p.ratio_clip);
+            const float sur = fminf(s1, s2);
+            const float elp = expf(lp);
+            const float ent = elp * lp;
+            const float g_lp = (-(s1 <= s2 ? s1 : 0.0f) + p.lambda_entropy * (ent + elp)) * invB;   // d united / d new_logprob
+            rv[6] = live ? g_lp * (-dd / std) : 0.0f;                            // d united / d a_avg
+            o_act = live ? (-sur + p.lambda_entropy * ent) * invB : 0.0f;
+            o_ent = live ? ent * invB : 0.0f;
+            g_asl = live ? g_lp * (dd * dd - 1.0f) : 0.0f;
+        } else {
+            const float e = rv[4] - rv[1];
+            const float ae = fabsf(e);
+            const float l1 = ae < 1.0f ? 0.5f * e * e : ae - 0.5f;               // SmoothL1Loss, beta = 1
+            rv[6] = live ? fminf(fmaxf(e, -1.0f), 1.0f) * invB * inv_cs : 0.0f;  // d united / d value
+            o_cri = live ? l1 * invB : 0.0f;
+        }
 #pragma unroll
         for (int o = 1; o < R; o <<= 1) {   // R is a power of two <= 32, the rows sit in one warp
             o_act += __shfl_xor_sync((1u << R) - 1u, o_act, o);
@@ -492,41 +503,34 @@ __global__ void __launch_bounds__(kRowsThreads, 1) ppo_rows_kernel(const StepPar
         if (tid == 0) {
             float *row = p.loss_ring + (size_t)(*p.step_dev % p.ring_len) * 4;
             atomicAdd(row + 0, o_act + o_cri * inv_cs);
-            atomicAdd(row + 1, o_act);
-            atomicAdd(row + 2, o_cri);
-            atomicAdd(row + 3, o_ent);
-            atomicAdd(p.g_astd, g_asl);
+            if (net == 0) { atomicAdd(row + 1, o_act); atomicAdd(row + 3, o_ent); atomicAdd(p.g_astd, g_asl); }
+            else atomicAdd(row + 2, o_cri);
         }
     }
     sync_compute();
 
-    net_backward<R>(ring, p.act, thA, sA, sZ, LA, sV + 6, kRowVals, sPart);
-    net_backward<R>(ring, p.cri, thC, sA + LAa, sZ + LAa, LA, sV + 7, kRowVals, sPart);
+    net_backward<R>(ring, d, th, sA, sZ, LA, sV + 6, kRowVals, sPart);
 
-    // output layers Linear(H -> 1): weight / bias gradients of this CTA's rows, straight into the accumulators
-    for (int j = tid; j < 2 * (p.act.H + 1); j += kThreads) {
-        const int net = j / (p.act.H + 1), k = j % (p.act.H + 1);
-        const float *Alast = net == 0 ? sA + (p.act.kind == PIME_ACTOR_MODULAR ? 3 : 2) * p.act.H : sA + LAa + 2 * p.cri.H;
+    // output layer Linear(H -> 1): weight / bias gradients of this CTA's rows, straight into the accumulators
+    for (int k = tid; k < d.H + 1; k += kThreads) {
+        const float *Alast = sA + (d.kind == PIME_ACTOR_MODULAR ? 3 : 2) * d.H;
         float g = 0.0f;
 #pragma unroll
-        for (int r = 0; r < R; ++r) g = fmaf(sV[r * kRowVals + 6 + net], k < p.act.H ? Alast[r * LA + k] : 1.0f, g);
+        for (int r = 0; r < R; ++r) g = fmaf(sV[r * kRowVals + 6], k < d.H ? Alast[r * LA + k] : 1.0f, g);
         atomicAdd(p.g_out + net * kOutAcc + k, g);
     }
 
     // rows -> scratch (inputs of the weight-gradient kernel)
+    float *ACT = net == 0 ? p.ACT_A : p.ACT_C, *DZ = net == 0 ? p.DZ_A : p.DZ_C;
     for (int r = 0; r < R; ++r) {
         const int b = b0 + r;
         if (b >= B) break;
-        for (int c = tid; c < LAa; c += kThreads) {
-            p.ACT_A[(size_t)b * LAa + c] = sA[r * LA + c];
-            p.DZ_A[(size_t)b * LAa + c] = sZ[r * LA + c];
+        for (int c = tid; c < LA; c += kThreads) {
+            ACT[(size_t)b * LA + c] = sA[r * LA + c];
+            DZ[(size_t)b * LA + c] = sZ[r * LA + c];
         }
-        for (int c = tid; c < LAc; c += kThreads) {
-            p.ACT_C[(size_t)b * LAc + c] = sA[r * LA + LAa + c];
-            p.DZ_C[(size_t)b * LAc + c] = sZ[r * LA + LAa + c];
-        }
-        if (tid < kXStride) p.X[(size_t)b * kXStride + tid] = sX[r * kXStride + tid];
-        if (tid < 2) p.DOUT[(size_t)b * 2 + tid] = sV[r * kRowVals + 6 + tid];
+        if (net == 0 && tid < kXStride) p.X[(size_t)b * kXStride + tid] = sX[r * kXStride + tid];
+        if (tid == 0) p.DOUT[(size_t)b * 2 + net] = sV[r * kRowVals + 6];
     }
 }
 
@@ -744,6 +748,7 @@ static void add_net_layers(StepParams &p, int net, const NetDims &d) {
 
 static void add_pass(StepParams &p, const NetDims &d, int src, bool transposed, int rows, int cols) {
     StreamPass &q = p.pass[p.n_passes++];
+    q.net = &d == &p.cri ? 1 : 0;
     q.off = d.theta_off + d.src[src]; q.transposed = transposed ? 1 : 0; q.rows = rows; q.cols = cols;
 }
 // the order in which net_forward / net_backward consume the ring
@@ -783,11 +788,12 @@ static int64_t work_floats_per_row(const StepParams &p) { return kXStride + 2 * 
 
 template <int R> static int launch_rows(const StepParams &p, cudaStream_t s) {
     constexpr int kStages = R <= 4 ? kMaxStages : 4;
-    const size_t smem = sizeof(float) * (size_t)(kStages * kSlabFloats + R * (kXStride + 2 * (p.act.LA + p.cri.LA) + kRowVals) + 8 + 1024 * R) +
+    const int LAmax = p.act.LA > p.cri.LA ? p.act.LA : p.cri.LA;
+    const size_t smem = sizeof(float) * (size_t)(kStages * kSlabFloats + R * (kXStride + 2 * LAmax + kRowVals) + 8 + 1024 * R) +
                         2 * kStages * sizeof(uint64_t);
     auto kern = ppo_rows_kernel<R>;
     PIME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(p.B + R - 1) / R, kRowsThreads, smem, s>>>(p);
+    kern<<<dim3((p.B + R - 1) / R, 2), kRowsThreads, smem, s>>>(p);
     PIME_LAUNCH_CHECK();
     return PIME_OK;
 }
@@ -860,7 +866,7 @@ int pime_ppo_step(const pime_ppo_args *a, void *stream) {
     p.DZ_C = w; w += B * p.cri.LA;
     p.DOUT = w;
     cudaStream_t s = (cudaStream_t)stream;
-    const int R = B <= 256 ? 2 : (B <= 512 ? 4 : 8);   // 64-128 CTAs at the reference's batch sizes; weights stream once per CTA
+    const int R = B <= 128 ? 2 : (B <= 256 ? 4 : 8);   // at most 128 CTAs (64 per net) up to 512 rows: one wave
     int rc = R == 2 ? ppo::launch_rows<2>(p, s) : (R == 4 ? ppo::launch_rows<4>(p, s) : ppo::launch_rows<8>(p, s));
     if (rc) return rc;
     ppo::ppo_wgrad_kernel<<<p.n_tiles, ppo::kThreads, 0, s>>>(p);
