@@ -27,3 +27,9 @@ extern "C" int pime_wt_rollout_host_f32(const pime_wt_config *cfg, int64_t n, co
     PIME_CUDA(cudaStreamSynchronize(s));
     return PIME_OK;
 }
+
+#ifdef PIME_PROFILE_WORKER
+extern "C" int pime_debug_worker_prof(double *out16) {
+    return cudaMemcpyFromSymbol(out16, pime::tc::g_worker_prof, 16 * sizeof(double)) == cudaSuccess ? 0 : -3;
+}
+#endif

@@ -416,6 +416,12 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) 
         : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+#ifdef PIME_PROFILE_WORKER
+__device__ double g_worker_prof[16];   // clocks of worker thread 0 of CTA 0 per segment of the modular pass (debug builds only)
+#define PIME_WTICK(k) { const long long c1_ = clock64(); wprof[k] += c1_ - c0_; c0_ = c1_; }
+#else
+#define PIME_WTICK(k)
+#endif
 template <int KIND, int H> struct Engine {
     using G = Geo<KIND, H>;
     uint8_t *sA, *sRing;
@@ -711,27 +717,45 @@ template <int KIND, int H> struct Engine {
             // Software pipeline over passes: the first epilogue of pass q (CUDA cores only) is wrapped around the last
             // epilogue of pass q-1, so that net.0 of pass q-1 (the one tensor-bound stretch) finishes in its shadow.
             uint32_t ep = 0;   // running count of A-writing epilogues (A tile = ep & 1), same sequence as the MMA warp
+#ifdef PIME_PROFILE_WORKER
+            long long wprof[16] = {0}, c0_ = clock64();
+#endif
             for (int q = 0; q < passes; ++q) {
                 const int g = q & 1;
                 mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);              // the owners have written this pass's observation
+                PIME_WTICK(0)
                 epilogue_l1i<0, G::NP / 2>(row, half, g, ep & 1u);          // tanh(integrator_net.0) (net_residual.py:154), first half
+                PIME_WTICK(1)
                 if (q > 0) {
                     wait_d();                                               // P3 of the previous pass: Db = net.0
+                    PIME_WTICK(2)
                     epilogue_dot(row, half, H, (q - 1) & 1);                // net.2 (:158) of the previous pass
+                    PIME_WTICK(3)
                 }
                 epilogue_l1i<G::NP / 2, G::NP>(row, half, g, ep & 1u);      // second half; feeds integrator_net.2 (:155)
+                PIME_WTICK(4)
                 ++ep;
                 mbar_wait(l1b_rdy, (uint32_t)q & 1u);                       // Db = other_net.0 (:151)
                 tc_fence_after();
+                PIME_WTICK(5)
                 epilogue<>(row, half, H, ep & 1u);                          // tanh(Db) -> A, feeds other_net.2 (:152)
+                PIME_WTICK(6)
                 ++ep;
                 mbar_wait(h_rdy, (uint32_t)q & 1u);                         // P1: Da[0:H/2] = integrator_net.2 (complete long ago)
                 tc_fence_after();
+                PIME_WTICK(7)
                 epilogue<0, G::NP / 2>(row, half, 0, ep & 1u);              // first half of cat' (:170) while other_net.2 finishes
+                PIME_WTICK(8)
                 wait_d();                                                   // P2: Da[H/2:H] = other_net.2
+                PIME_WTICK(9)
                 epilogue<G::NP / 2, G::NP>(row, half, 0, ep & 1u);          // second half of cat', feeds net.0 (:157)
+                PIME_WTICK(10)
                 ++ep;
             }
+#ifdef PIME_PROFILE_WORKER
+            if (blockIdx.x == 0 && threadIdx.x == 0)
+                for (int k = 0; k < 11; ++k) g_worker_prof[k] = (double)wprof[k] / passes;
+#endif
             wait_d();
             epilogue_dot(row, half, H, (passes - 1) & 1);
         } else {
