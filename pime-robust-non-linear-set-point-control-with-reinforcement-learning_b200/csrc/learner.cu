@@ -74,6 +74,7 @@ struct StepParams {
     int *step_dev;            // Adam step count so far (the step being taken is *step_dev + 1)
     unsigned *ticket;
     float *g_astd;            // accumulated gradient of a_std_log
+    float *adam_c;            // [2]: lr / bias_correction1 and 1 / sqrt(bias_correction2) of the step being taken (written by the rows kernel)
     float *g_out;             // [2][kOutAcc]: accumulated gradients of the two output layers Linear(H -> 1): weight[H], bias
     float *X, *ACT_A, *DZ_A, *ACT_C, *DZ_C, *DOUT;
     float *loss_ring;
@@ -378,6 +379,8 @@ __device__ __forceinline__ void net_backward(Ring &ring, const NetDims &d, const
     sync_compute();
 }
 
+__device__ __forceinline__ void adam_prepare(const StepParams &p);
+
 // grid = (row tiles, 2): blockIdx.y = 0 runs the actor (forward, policy objectives, backward), 1 the critic.  The two
 // nets share nothing but the gathered rows (obj_united = obj_actor + obj_critic / (std + 1e-5) is a sum), so splitting
 // them halves the chain of dependent layers a CTA walks through.
@@ -426,6 +429,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) ppo_rows_kernel(const StepPar
     const int B = p.B;
     const int b0 = blockIdx.x * R;
 
+    if (blockIdx.x == 0 && net == 0 && tid == 0) adam_prepare(p);
     float inv_cs = 0.0f;
     if (net == 1) {   // r_sum.std() of the minibatch (agent.py:652; unbiased), two passes
         float s = 0.0f;
@@ -539,11 +543,17 @@ __global__ void __launch_bounds__(kRowsThreads, 1) ppo_rows_kernel(const StepPar
 struct AdamCoef {
     float lr_bc1, inv_sqrt_bc2, one_m_b1, b2, one_m_b2, eps;
 };
-__device__ __forceinline__ AdamCoef adam_coef(const StepParams &p, int t) {
-    AdamCoef c;
+// the two step-dependent coefficients (double-precision pow) are computed once per step, by one thread of the rows kernel
+__device__ __forceinline__ void adam_prepare(const StepParams &p) {
+    const int t = *p.step_dev + 1;
     const double bc1 = 1.0 - pow((double)p.beta1, (double)t), bc2 = 1.0 - pow((double)p.beta2, (double)t);
-    c.lr_bc1 = (float)((double)p.lr / bc1);
-    c.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    p.adam_c[0] = (float)((double)p.lr / bc1);
+    p.adam_c[1] = (float)(1.0 / sqrt(bc2));
+}
+__device__ __forceinline__ AdamCoef adam_coef(const StepParams &p) {
+    AdamCoef c;
+    c.lr_bc1 = p.adam_c[0];
+    c.inv_sqrt_bc2 = p.adam_c[1];
     c.one_m_b1 = 1.0f - p.beta1; c.b2 = p.beta2; c.one_m_b2 = 1.0f - p.beta2; c.eps = p.eps;
     return c;
 }
@@ -649,7 +659,7 @@ __global__ void __launch_bounds__(kThreads) ppo_wgrad_kernel(const StepParams p)
     }
 
     const int t = *p.step_dev + 1;
-    const AdamCoef c = adam_coef(p, t);
+    const AdamCoef c = adam_coef(p);
     auto apply = [&](int idx, int idx_t, float g) {
         if (p.grad_out) { p.grad_out[idx] = g; return; }
         float m = p.m[idx], v = p.v[idx];
@@ -856,6 +866,7 @@ int pime_ppo_step(const pime_ppo_args *a, void *stream) {
     p.lr = a->lr; p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps;
     p.step_dev = (int *)a->state; p.ticket = (unsigned *)a->state + 1; p.g_astd = (float *)a->state + 2;
     p.g_out = (float *)a->state + 16;
+    p.adam_c = (float *)a->state + 8;
     p.loss_ring = a->loss_ring; p.ring_len = a->ring_len;
     const int64_t B = a->batch;
     float *w = a->work;
