@@ -28,8 +28,9 @@
 // Layers (reference elegantrl/net_residual.py), Da = TMEM columns [0,H), Db = [H,2H):
 //   modular (:138-205): software-pipelined over passes, two A tiles / barrier sets used alternately by consecutive
 //                       epilogues (see Engine::worker_loop):  E1 tanh(integrator_net.0) on the CUDA cores, wrapped around
-//                       the previous pass's last epilogue;  P1 integrator_net.2 -> Da[0:H/2];  other_net.0 -> Db as soon
-//                       as the previous pass has released Db;  E2 tanh(Db);  P2 other_net.2 -> Da[H/2:H];  E3 tanh(cat'),
+//                       the previous pass's last epilogue (a thread owns one 8-column chunk and walks down the rows, its
+//                       (w, b) pairs in registers);  other_net.0 -> Db as soon as the previous pass has released Db;
+//                       P1 integrator_net.2 -> Da[0:H/2];  E2 tanh(Db);  P2 other_net.2 -> Da[H/2:H];  E3 tanh(cat'),
 //                       cat' = Da = [integrator | other] (net.0's input columns are rotated in the pack);  P3 net.0 -> Db;
 //                       E4 tanh(Db) . net.2 during the NEXT pass's E1.
 //   plain (:6-66) / CriticAdv (net.py:274-277): P0 net.0 -> X, P1 net.2 -> Y, P2 net.4 -> X, net.6 in the epilogue of X,
@@ -145,11 +146,6 @@ inline bool emit_gemm(PackLayout &L, const GemmSpec &g) {
     return true;
 }
 
-// K=16 slice at which the MMA program of integrator_net.2 is interrupted to issue other_net.0 (see Engine::mma_loop)
-__host__ __device__ constexpr int p1_split_k16(int H) {
-    const int K16 = H / 16, kpb = blk_k16(H / 2, K16);
-    return ((K16 / 2) / kpb) * kpb;
-}
 
 inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
     const int H = c.mid_dim, S = c.state_dim, D = c.integrator_dim;
@@ -183,14 +179,11 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
         L.nin = 4; L.nterms = 3; L.KP = 16;   // inputs (o0,o1,o2,I): 3 x 4 + 2 = 14 <= 16
         // The integrator branch runs first and its one-input first layer runs on the CUDA cores (header, kL1iOff), so a
         // pass can start while the previous one still owns both TMEM buffers.  cat is therefore [integrator | other]
-        // and net.0's input columns are rotated by H/2 to match.  other_net.0 is issued in the middle of
-        // integrator_net.2's K loop (p1_split_k16), right after the previous pass has released Db.
-        const int ks = p1_split_k16(H);
+        // and net.0's input columns are rotated by H/2 to match.  other_net.0 goes first: it is issued as soon as the
+        // previous pass has released Db, in the shadow of the CUDA-core epilogue that feeds integrator_net.2.
         L.l1i_w = L.src[4]; L.l1i_b = L.src[5];
-        bias(Hh, Hh, L.src[7], Da);                                        // P1 integrator_net.2 -> Da[0:H/2]
-        if (ks > 0) hid(Hh, Hh, L.src[6], Da, 0, 0, ks);                   //    first K part
-        l1(H, L.src[0], So, L.src[1], 0, So, Db);                          //    other_net.0 -> Db
-        if (ks < HK) hid(Hh, Hh, L.src[6], Da, 0, ks, HK);                 //    integrator_net.2, second K part
+        l1(H, L.src[0], So, L.src[1], 0, So, Db);                          // other_net.0 -> Db
+        bias(Hh, Hh, L.src[7], Da); hid(Hh, Hh, L.src[6], Da);             // P1 integrator_net.2 -> Da[0:H/2]
         bias(Hh, Hh, L.src[3], Da + Hh); hid(Hh, Hh, L.src[2], Da + Hh);   // P2 other_net.2 -> Da[H/2:H]
         bias(H, H, L.src[9], Db); hid(H, H, L.src[8], Db, Hh);             // P3 net.0 on cat' = [integrator | other] -> Db
         L.out_w = L.src[10]; L.out_b = L.src[11];                          // net.2: fp32 dot product inside the last epilogue
@@ -576,15 +569,15 @@ template <int KIND, int H> struct Engine {
             const uint32_t g = (uint32_t)q & 1u;
             const uint32_t obs = (uint32_t)G::ObsOff + g * (uint32_t)G::ObsGroupBytes;
             if constexpr (G::kModular) {
-                constexpr int KS = p1_split_k16(H);
-                // P1: integrator_net.2 -> Da[0:H/2] behind the CUDA-core epilogue of integrator_net.0.  Da is free: the
-                // third epilogue of the previous pass was consumed piece by piece by its net.0 MMAs (program order).
-                layer<Hh, 0, KS, true>(Da, (ep >> 1) & 1u, ep & 1u, 0, nullptr, nullptr);   // bias block + K slices below the split
-                mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);            // the group's observation operand is written
-                if (q > 0) mbar_wait(out_rdy, ((uint32_t)q - 1u) & 1u);    // last epilogue of the previous pass has read Db
+                // other_net.0 -> Db as soon as the owners have written the observation and the previous pass's last epilogue
+                // has read Db: it runs in the shadow of the CUDA-core epilogue of integrator_net.0.
+                mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);
+                if (q > 0) mbar_wait(out_rdy, ((uint32_t)q - 1u) & 1u);
                 tc_fence_after();
-                blk<H, true>(obs, 1, Db, l1b_rdy);                         // other_net.0 -> Db, in the shadow of the epilogue above
-                layer<Hh, KS, H / 16, false>(Da, (ep >> 1) & 1u, ep & 1u, 0, h_rdy, nullptr);
+                blk<H, true>(obs, 1, Db, l1b_rdy);
+                // P1: integrator_net.2 -> Da[0:H/2], once that epilogue has written its rows (all chunks arrive together).
+                // Da is free: the third epilogue of the previous pass was consumed piece by piece by its net.0 MMAs.
+                layer<Hh>(Da, (ep >> 1) & 1u, ep & 1u, 0, h_rdy, nullptr);
                 ++ep;
                 layer<Hh>(Da + Hh, (ep >> 1) & 1u, ep & 1u, 0, d_ready, nullptr);   // P2: other_net.2 -> Da[H/2:H], behind the epilogue of Db
                 ++ep;
@@ -653,28 +646,46 @@ template <int KIND, int H> struct Engine {
         }
     }
     // modular: tanh(integrator_net.0) straight from the fp32 integrated error (one input: w * I + b on the FMA pipe);
-    // needs neither TMEM nor the tensor pipe, so it runs while the previous pass's net.0 is still accumulating.
-    template <int JB, int JE>
-    __device__ __forceinline__ void epilogue_l1i(int row, int half, int g, uint32_t abuf) {
-        if constexpr (JB < JE) {
-            const float I = sI[g * kRows + row];
-            float x[2][16];
-            auto piece = [&](int j, float (&y)[16]) {
-                const float4 *wb = reinterpret_cast<const float4 *>(sL1i + 2 * (32 * j + 16 * half));
+    // needs neither TMEM nor the tensor pipe, so it runs while the previous pass's net.0 is still accumulating.  Here a
+    // thread owns ONE 8-column chunk (its 8 (w, b) pairs stay in registers for the call) and walks down the rows, RL rows
+    // apart: one 4-byte shared-memory load per 8 activations instead of one 16-byte load per 2, which matters because the
+    // shared-memory pipe is shared with the operand fetch of the MMAs running underneath.  PART 0 / 1 = upper / lower
+    // half of the rows; the chunk barriers are signalled once, at the end of PART 1.
+    template <int PART>
+    __device__ __forceinline__ void epilogue_l1i(int tid, int g, uint32_t abuf) {
+        constexpr int CH = H / 8, RL = kWorkerThreads / CH, IT = kRows / RL, ITB = PART * (IT / 2), ITE = PART ? IT : IT / 2;
+        const int chunk = tid / RL, rl = tid % RL;
+        float w[8], b[8];
+        {
+            const float4 *wb = reinterpret_cast<const float4 *>(sL1i + 16 * chunk);   // (w, b) pairs of columns 8 chunk .. +8
 #pragma unroll
-                for (int e = 0; e < 16; e += 2) {
-                    const float4 t = wb[e / 2];   // (w_e, b_e, w_{e+1}, b_{e+1})
-                    y[e] = act_pinned<false>(fmaf(t.x, I, t.y));
-                    y[e + 1] = act_pinned<false>(fmaf(t.z, I, t.w));
-                }
-            };
-            piece(JB, x[0]);
-#pragma unroll
-            for (int j = JB; j < JE; ++j) {
-                const int cur = (j - JB) & 1;
-                if (j + 1 < JE) piece(j + 1, x[cur ^ 1]);
-                store_piece(abuf, row, half, j, x[cur]);
+            for (int e = 0; e < 4; ++e) {
+                const float4 t = wb[e];
+                w[2 * e] = t.x; b[2 * e] = t.y; w[2 * e + 1] = t.z; b[2 * e + 1] = t.w;
             }
+        }
+        const float *Ig = sI + g * kRows + rl;
+        float x[2][8];
+        auto rowvals = [&](int it, float (&y)[8]) {
+            const float I = Ig[RL * it];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = act_pinned<false>(fmaf(w[e], I, b[e]));
+        };
+        if constexpr (ITB < ITE) {
+            rowvals(ITB, x[0]);
+#pragma unroll
+            for (int it = ITB; it < ITE; ++it) {
+                const int cur = (it - ITB) & 1;
+                if (it + 1 < ITE) rowvals(it + 1, x[cur ^ 1]);
+                const float(&v)[8] = x[cur];
+                a_store8(abuf, rl + RL * it, chunk, pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+            }
+        }
+        if constexpr (PART == 1) {
+            tc_fence_before();
+            fence_proxy_async();
+#pragma unroll
+            for (int c = 0; c < (G::NP + 1) / 2; ++c) mbar_arrive(&a_rdy[abuf * kMaxChunks + c]);
         }
     }
 
@@ -724,7 +735,7 @@ template <int KIND, int H> struct Engine {
                 const int g = q & 1;
                 mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);              // the owners have written this pass's observation
                 PIME_WTICK(0)
-                epilogue_l1i<0, G::NP / 2>(row, half, g, ep & 1u);          // tanh(integrator_net.0) (net_residual.py:154), first half
+                epilogue_l1i<0>(tid, g, ep & 1u);                           // tanh(integrator_net.0) (net_residual.py:154), upper rows
                 PIME_WTICK(1)
                 if (q > 0) {
                     wait_d();                                               // P3 of the previous pass: Db = net.0
@@ -732,7 +743,7 @@ template <int KIND, int H> struct Engine {
                     epilogue_dot(row, half, H, (q - 1) & 1);                // net.2 (:158) of the previous pass
                     PIME_WTICK(3)
                 }
-                epilogue_l1i<G::NP / 2, G::NP>(row, half, g, ep & 1u);      // second half; feeds integrator_net.2 (:155)
+                epilogue_l1i<1>(tid, g, ep & 1u);                           // lower rows; feeds integrator_net.2 (:155)
                 PIME_WTICK(4)
                 ++ep;
                 mbar_wait(l1b_rdy, (uint32_t)q & 1u);                       // Db = other_net.0 (:151)

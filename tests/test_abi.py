@@ -143,9 +143,7 @@ def _device_program(kind, H, S):
         return out
 
     if kind == 1:   # modular
-        kpb = blk_k16(Hh, K16)
-        ks = ((K16 // 2) // kpb) * kpb
-        return (layer(Hh, Da, 0, ks, True) + [(H, 1, Db)] + layer(Hh, Da, ks, K16, False) + layer(Hh, Da + Hh) + layer(H, Db))
+        return [(H, 1, Db)] + layer(Hh, Da) + layer(Hh, Da + Hh) + layer(H, Db)
     nin = 16 if S <= 16 else 32
     KP = ((((3 if S <= 10 else 2) * nin + 2) + 15) // 16) * 16
     kpb = blk_k16(H, 5)
