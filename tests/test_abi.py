@@ -166,3 +166,27 @@ def test_pack_block_list_matches_the_kernels_static_mma_program(L, kind, S, H):
     assert all(0 < s <= 16384 and s == N * k * 32 for s, (N, k, _) in zip(sizes, got))
     assert sum(sizes) + 4096 == L.lib().pime_actor_pack_bytes(C.byref(cfg))
     assert all(d + N <= 2 * H for N, _, d in got)              # accumulators stay inside the two TMEM buffers
+
+
+@pytest.mark.parametrize("kind,S,H", [(1, 4, 256), (1, 3, 128), (1, 2, 32), (0, 3, 64), (0, 30, 256), (0, 12, 128)])
+def test_ppo_learner_layout_is_host_computable(L, kind, S, H):
+    """pime_ppo_theta_layout / pime_ppo_work_floats need no GPU: theta = [actor | pad | critic | a_std_log] with the critic
+    on a 16-byte boundary (its hidden-layer matrices are streamed with cp.async.bulk), scratch = per-row activations and
+    pre-activation gradients of both nets + the gathered state row + the two output gradients."""
+    cfg = L.ActorConfig(kind=kind, state_dim=S, mid_dim=H, integrator_dim=1 if kind == 1 else 0)
+    cri = L.ActorConfig(kind=2, state_dim=S, mid_dim=H, integrator_dim=0)
+    pa, pc = L.lib().pime_actor_param_count(C.byref(cfg)), L.lib().pime_actor_param_count(C.byref(cri))
+    if kind == 1:
+        assert pa == H * (S - 1) + H + (H // 2) * H + H // 2 + H + H + (H // 2) * H + H // 2 + H * H + H + H + 1
+    else:
+        assert pa == H * S + H + 2 * (H * H + H) + H + 1
+    assert pc == H * S + H + 2 * (H * H + H) + H + 1
+    lay = (C.c_int64 * 3)()
+    assert L.lib().pime_ppo_theta_layout(C.byref(cfg), lay) == 0
+    assert lay[0] % 4 == 0 and pa <= lay[0] < pa + 4 and lay[1] == lay[0] + pc and lay[2] == lay[1] + 1
+    assert L.lib().pime_ppo_theta_count(C.byref(cfg)) == lay[2]
+    la = (4 if kind == 1 else 3) * H + 3 * H
+    for B in (2, 37, 256, 4096):
+        assert L.lib().pime_ppo_work_floats(C.byref(cfg), C.c_int32(B)) == B * (32 + 2 * la + 2)
+    bad = L.ActorConfig(kind=kind, state_dim=S, mid_dim=48, integrator_dim=1 if kind == 1 else 0)
+    assert L.lib().pime_ppo_theta_count(C.byref(bad)) == -1
