@@ -50,7 +50,7 @@ TANH_PER_STEP = {("modular", 256, 4): 1025, ("modular", 128, 3): 513, ("plain", 
 NCU_DRAM_BYTES_PER_LAUNCH = {("wt", 1 << 20, 200): 6.7561e9}   # profiles/r01_ncu_summary.md (algorithmic: 6.71e9 replay rows)
 NCU_DRAM_BYTES_STEP = {"wt": 1.8720e9, "ph": 1.7354e9}   # *_step_kernel<float>, 2^25 envs (algorithmic 1.913e9 / 1.778e9)
 WT_STEP_BYTES_F32 = 57   # 36 B read + 21 B written per env-step, SoA fp32
-PH_STEP_BYTES_F32 = 53
+PH_STEP_BYTES_F32 = 69   # x, A, B are fp64 in the float flavour: read x8 r4 I4 A8 B8 C4 a4 t4 = 44, write x8 y4 I4 t4 rew4 done1 = 25
 
 
 def parse():

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PIME_B200_ABI_VERSION 2
+#define PIME_B200_ABI_VERSION 3
 
 enum {
     PIME_OK = 0,
@@ -136,17 +136,22 @@ typedef struct pime_ph_config {
     double x_lo, x_hi, r_lo, r_hi;          /* reset: x ~ U(0,50), r ~ U(3,11) (ph.py:420-424)           */
 } pime_ph_config;
 
+/* Precision of the float flavour: x, last_x, A and B are DOUBLE arrays in both flavours.  y is a staircase in x
+ * (100 000-entry table), so the reaction invariant, the discretised system and the three-operation index
+ * rint(C*x*1e5) are kept in fp64 -- the *_f32 entry points then pick the same table entry as the *_f64 ones on identical
+ * (x, A, B, C, action); every other array of the float flavour (y, r, I, C = qc_V, qww_V, qc_V, ep_return) is float. */
 typedef struct pime_ph_state {
-    void *x;              /* reaction-invariant state                                                    */
+    void *x;              /* reaction-invariant state; double[n] in BOTH flavours                        */
     void *y;              /* pH                                                                          */
     void *r, *I;
-    void *A, *B, *C;      /* discretised system dsys.A/B/C (update_system ph.py:114-121)                 */
+    void *A, *B, *C;      /* discretised system dsys.A/B/C (update_system ph.py:114-121); A, B: double[n] in
+                             BOTH flavours, C: state dtype                                               */
     void *qww_V, *qc_V;   /* ensemble parameters (get_changable_parameters ph.py:268-270)                */
     int32_t *t;
     uint32_t *episode;
     void *ep_return;
-    void *last_x;         /* state at the last time-limit step (ph.py:345-346); NaN = None.  Required when
-                             cfg.reset_from_last_state, else may be NULL                                 */
+    void *last_x;         /* state at the last time-limit step (ph.py:345-346); double[n], NaN = None.  Required
+                             when cfg.reset_from_last_state, else may be NULL                            */
 } pime_ph_state;
 
 void pime_ph_default_config(pime_ph_config *cfg); /* registered PH1D...Integrator-SqaureDistance-v35 values */
@@ -244,7 +249,8 @@ typedef struct pime_rollout_args {
     double reward_scale, gamma;
     uint64_t seed, env_offset;
     uint32_t tick0;                 /* RNG tick of the first step (global step counter)                      */
-    uint32_t reserved0;
+    uint32_t keep_params;           /* 1: the in-kernel reset keeps the ensemble parameters (if_reset_all=False ->
+                                       reset_r, nonlinear_watertank.py:935-939 / ph.py:441-445); 0: reset_all          */
     const float *eps;               /* [T][n] exploration noise; NULL: Philox N(0,1) (0 when deterministic)  */
     const void *pnoise1, *pnoise2;  /* [T][n] process noise (state dtype); NULL: Philox or none (see step)   */
     float *buf_state;               /* [T][n][S] float32 replay states, may be NULL                          */

@@ -60,7 +60,7 @@ class RolloutArgs(C.Structure):
     _fields_ = [("actor", C.POINTER(ActorConfig)), ("actor_pack", vp), ("a_std_log", C.c_float), ("deterministic", C.c_int32),
                 ("priorK_host", C.POINTER(C.c_double)), ("T", C.c_int32), ("auto_reset", C.c_int32),
                 ("reward_scale", C.c_double), ("gamma", C.c_double), ("seed", C.c_uint64), ("env_offset", C.c_uint64),
-                ("tick0", C.c_uint32), ("reserved0", C.c_uint32), ("eps", vp), ("pnoise1", vp), ("pnoise2", vp),
+                ("tick0", C.c_uint32), ("keep_params", C.c_uint32), ("eps", vp), ("pnoise1", vp), ("pnoise2", vp),
                 ("buf_state", vp), ("buf_other", vp), ("env_action", vp), ("stats", vp), ("status", vp)]
 
 

@@ -12,7 +12,7 @@ constexpr int kMaxS = 32;
 
 struct RolloutParams {
     int64_t n;
-    int T, deterministic, auto_reset, has_actor;
+    int T, deterministic, auto_reset, has_actor, keep_params;
     float a_std;            // exp(a_std_log)
     double reward_scale, gamma;
     uint64_t seed, env_offset;
@@ -108,11 +108,11 @@ template <typename T, bool STACK> struct WtGlue {
         if (last_h1) { last_h1[i] = v.e.h1; last_h2[i] = v.e.h2; }
     }
     // the in-kernel reset always follows a `done`, so "the levels of the last finished episode" are the current ones
-    __device__ __forceinline__ bool reset(Env &v, uint64_t seed, uint64_t index) const {
+    __device__ __forceinline__ bool reset(Env &v, uint64_t seed, uint64_t index, bool resample) const {
         double u[6];
         reset_uniforms(seed, index, v.episode, u);
         const T k1 = v.e.h1, k2 = v.e.h2;
-        wt_reset(c, v.e, u, true);
+        wt_reset(c, v.e, u, resample);
         if (c.from_last) { v.e.h1 = k1; v.e.h2 = k2; }
         v.episode += 1;
         if constexpr (STACK) {
@@ -130,7 +130,8 @@ template <typename T> struct PhGlue {
     static constexpr int kObsMax = 3;
     PhConst<T> c;
     const T *table;
-    T *x, *y, *r, *I, *A, *B, *C, *qww, *qc, *ep_return, *last_x;
+    double *x, *A, *B, *last_x;   // fp64 in both flavours (plants.cuh)
+    T *y, *r, *I, *C, *qww, *qc, *ep_return;
     int32_t *t;
     uint32_t *episode;
 
@@ -170,10 +171,10 @@ template <typename T> struct PhGlue {
     __device__ __forceinline__ void record_done(const Env &v, int64_t i) const {   // ph.py:345-346
         if (last_x) last_x[i] = v.e.x;
     }
-    __device__ __forceinline__ bool reset(Env &v, uint64_t seed, uint64_t index) const {
+    __device__ __forceinline__ bool reset(Env &v, uint64_t seed, uint64_t index, bool resample) const {
         double u[6];
         reset_uniforms(seed, index, v.episode, u);
-        bool ok = ph_reset(c, table, v.e, v.qww, v.qc, u, true, c.from_last ? v.e.x : nan_of<T>());
+        bool ok = ph_reset(c, table, v.e, v.qww, v.qc, u, resample, c.from_last ? v.e.x : nan_of<double>());
         v.episode += 1;
         return ok;
     }
@@ -264,8 +265,8 @@ template <typename Plant> struct Stepper {
                 s_err += (double)plant.tracking_error(env);
             }
         }
-        if (done && rp.auto_reset) {  // env.reset() -> reset_all(): new ensemble member (T4 in SURVEY.md)
-            if (!plant.reset(env, rp.seed, rp.env_offset + (uint64_t)ii)) fault = true;
+        if (done && rp.auto_reset) {  // env.reset() -> reset_all(): new ensemble member (T4 in SURVEY.md), or reset_r()
+            if (!plant.reset(env, rp.seed, rp.env_offset + (uint64_t)ii, rp.keep_params == 0)) fault = true;
             env.ret = (T)0;
         }
     }
@@ -430,6 +431,7 @@ inline int fill_rollout_params(const pime_rollout_args *a, int64_t n, int S, Rol
     rp = RolloutParams{};
     rp.n = n; rp.T = a->T; rp.deterministic = a->deterministic; rp.auto_reset = a->auto_reset;
     rp.has_actor = a->actor != nullptr;
+    rp.keep_params = a->keep_params != 0;
     rp.a_std = expf(a->a_std_log);
     rp.reward_scale = a->reward_scale; rp.gamma = a->gamma; rp.seed = a->seed; rp.env_offset = a->env_offset; rp.tick0 = a->tick0;
     rp.S = S;

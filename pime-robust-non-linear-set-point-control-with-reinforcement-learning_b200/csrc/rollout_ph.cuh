@@ -23,9 +23,9 @@ int ph_rollout_impl(const pime_ph_config *cfg, const T *table, int64_t n, const 
     PhGlue<T> g;
     g.c = make_ph_const<T>(*cfg);
     g.table = table;
-    g.x = (T *)st->x; g.y = (T *)st->y; g.r = (T *)st->r; g.I = (T *)st->I;
-    g.A = (T *)st->A; g.B = (T *)st->B; g.C = (T *)st->C; g.qww = (T *)st->qww_V; g.qc = (T *)st->qc_V;
-    g.ep_return = (T *)st->ep_return; g.last_x = (T *)st->last_x; g.t = st->t; g.episode = st->episode;
+    g.x = (double *)st->x; g.y = (T *)st->y; g.r = (T *)st->r; g.I = (T *)st->I;
+    g.A = (double *)st->A; g.B = (double *)st->B; g.C = (T *)st->C; g.qww = (T *)st->qww_V; g.qc = (T *)st->qc_V;
+    g.ep_return = (T *)st->ep_return; g.last_x = (double *)st->last_x; g.t = st->t; g.episode = st->episode;
     cudaStream_t s = (cudaStream_t)stream;
     if (!rp.has_actor) return launch_rollout_prior<PhGlue<T>>(g, rp, s);
     if (args->actor->kind == PIME_ACTOR_MODULAR) {

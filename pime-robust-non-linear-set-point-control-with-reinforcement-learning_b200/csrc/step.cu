@@ -1,6 +1,8 @@
 // step.cu -- stand-alone (gym-API) kernels: reset / step for both plants, titration table, prior action,
 // GAE scan, episode statistics.  One thread per env, SoA state, grid-stride over a grid sized in multiples of
 // the SM count.  HBM-bound in fp32 (57 B / env-step water tank, 53 B pH).
+#include <initializer_list>
+
 #include "plants.cuh"
 
 namespace pime {
@@ -52,12 +54,13 @@ __device__ __forceinline__ void wt_write_obs(const WtConst<T> &c, const WtPtrs<T
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kBlock) wt_step_kernel(WtConst<T> c, int64_t n, WtPtrs<T> p, const T *__restrict__ action,
-                                                         const T *__restrict__ noise1, const T *__restrict__ noise2,
-                                                         uint64_t seed, uint64_t env_offset, uint32_t tick, T *obs_out,
-                                                         T *__restrict__ reward, uint8_t *__restrict__ done) {
+__global__ void __launch_bounds__(kBlock) wt_step_kernel(WtConst<T> c, int64_t i_begin, int64_t n, WtPtrs<T> p,
+                                                         const T *__restrict__ action, const T *__restrict__ noise1,
+                                                         const T *__restrict__ noise2, uint64_t seed, uint64_t env_offset,
+                                                         uint32_t tick, T *obs_out, T *__restrict__ reward,
+                                                         uint8_t *__restrict__ done) {
     const bool integ = c.obs_mode == PIME_WT_OBS_INTEGRATOR;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = i_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         WtEnv<T> e;
         e.h1 = p.h1[i]; e.h2 = p.h2[i]; e.r = p.r[i];
         e.I = integ ? p.I[i] : (T)0;
@@ -86,6 +89,129 @@ __global__ void __launch_bounds__(kBlock) wt_step_kernel(WtConst<T> c, int64_t n
         if (dn && p.last_h1) { p.last_h1[i] = e.h1; p.last_h2[i] = e.h2; }                      // :819-821
         wt_write_obs(c, p, e, i, n, obs_out, false);
     }
+}
+
+
+// ---- float flavour, goal / integrator observation: FOUR consecutive envs per thread.  The SoA arrays are contiguous, so
+// a thread's four envs are one 16-byte element of every array (float4 / int4 / uchar4 loads and stores; a warp moves 512
+// contiguous bytes per array), and the four independent 20-sub-step Euler chains are interleaved so that the MUFU.SQRT
+// latency of one chain is covered by the other three.  57 B of HBM traffic per env-step against 40 MUFU ops: the HBM floor
+// and the MUFU floor of this kernel coincide, hence nothing may be left serialised.
+constexpr int kVec = 4;
+constexpr int kVecBlock = 128;
+
+__device__ __forceinline__ float4 ld4(const float *p, int64_t g) { return __ldcs(reinterpret_cast<const float4 *>(p) + g); }
+__device__ __forceinline__ void st4(float *p, int64_t g, const float (&v)[4]) {
+    __stcs(reinterpret_cast<float4 *>(p) + g, make_float4(v[0], v[1], v[2], v[3]));
+}
+__device__ __forceinline__ void unpack4(const float4 &v, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+
+__global__ void __launch_bounds__(kVecBlock) wt_step_vec4_kernel(WtConst<float> c, int64_t groups, int64_t n, WtPtrs<float> p,
+                                                                 const float *__restrict__ action, const float *__restrict__ noise1,
+                                                                 const float *__restrict__ noise2, uint64_t seed, uint64_t env_offset,
+                                                                 uint32_t tick, float *obs_out, float *__restrict__ reward,
+                                                                 uint8_t *__restrict__ done) {
+    const bool integ = c.obs_mode == PIME_WT_OBS_INTEGRATOR;
+    const bool philox = noise1 == nullptr && c.noise_scale > 0.0f;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        float h1[4], h2[4], r[4], I[4], a1[4], a2[4], Kp[4], act[4], nz1[4], nz2[4], rew[4];
+        int t[4];
+        unpack4(ld4(p.h1, g), h1); unpack4(ld4(p.h2, g), h2); unpack4(ld4(p.r, g), r);
+        unpack4(ld4(p.a1, g), a1); unpack4(ld4(p.a2, g), a2); unpack4(ld4(p.Kp, g), Kp);
+        unpack4(ld4(action, g), act);
+        if (integ) unpack4(ld4(p.I, g), I);
+        else I[0] = I[1] = I[2] = I[3] = 0.0f;
+        {
+            const int4 tv = __ldcs(reinterpret_cast<const int4 *>(p.t) + g);
+            t[0] = tv.x; t[1] = tv.y; t[2] = tv.z; t[3] = tv.w;
+        }
+        if (noise1) {
+            unpack4(ld4(noise1, g), nz1); unpack4(ld4(noise2, g), nz2);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                nz1[e] = nz2[e] = 0.0f;
+                if (philox) {  // get_noise (:271-272), Philox instead of numpy's global stream
+                    const Philox4 w = philox4x32_10(seed, env_offset + (uint64_t)(4 * g + e), tick, kStreamStep);
+                    float z0, z1;
+                    box_muller(w.v[0], w.v[1], z0, z1);
+                    nz1[e] = z0 * c.noise_scale;
+                    nz2[e] = z1 * c.noise_scale;
+                }
+            }
+        }
+        // the four Euler chains, sub-step by sub-step (same arithmetic as wt_integrate<float>)
+        float k1[4], k2a[4], k2b[4], b1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float u = wt_u(c, act[e]);                                                    // :260
+            k1[e] = -a1[e] * c.sq2G_dt_over_A1;
+            k2a[e] = a1[e] * c.sq2G_dt_over_A2;
+            k2b[e] = -a2[e] * c.sq2G_dt_over_A2;
+            b1[e] = Kp[e] * u * c.dt_over_A1;
+        }
+#pragma unroll 2
+        for (int k = 0; k < c.n_discrete; ++k) {
+            float s1[4], s2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { s1[e] = Num<float>::sqrt(h1[e]); s2[e] = Num<float>::sqrt(h2[e]); }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float n1 = fmaf(k1[e], s1[e], h1[e] + b1[e]);
+                const float n2 = fmaf(k2a[e], s1[e], fmaf(k2b[e], s2[e], h2[e]));
+                h1[e] = fmaxf(n1, 0.0f);
+                h2[e] = fmaxf(n2, 0.0f);
+            }
+        }
+        uint32_t dn4 = 0;
+        bool any_done = false;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            t[e] += 1;                                                                          // :801
+            h1[e] = fmaxf(h1[e] + nz1[e], 0.0f);                                                // :810-813
+            h2[e] = fmaxf(h2[e] + nz2[e], 0.0f);
+            float rw = reward_of<float>(c.reward_type, fabsf(h2[e] - r[e]), c.z1, c.thr);       // :815
+            const bool dn = t[e] >= c.max_step;                                                 // :816-821
+            if (integ) {
+                const float integ_raw = I[e] + (r[e] - h2[e]);                                  // :822-823
+                rw = rw + (-c.Ipunish) * fabsf(integ_raw);                                      // :824
+                I[e] = clampT(integ_raw, -c.Imax, c.Imax);                                      // :825
+            }
+            rew[e] = rw;
+            dn4 |= (dn ? 1u : 0u) << (8 * e);
+            any_done |= dn;
+        }
+        st4(p.h1, g, h1); st4(p.h2, g, h2);
+        if (integ) st4(p.I, g, I);
+        __stcs(reinterpret_cast<int4 *>(p.t) + g, make_int4(t[0], t[1], t[2], t[3]));
+        if (p.ep_return) {
+            float er[4];
+            unpack4(ld4(p.ep_return, g), er);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) er[e] += rew[e];
+            st4(p.ep_return, g, er);
+        }
+        st4(reward, g, rew);
+        __stcs(reinterpret_cast<uint32_t *>(done) + g, dn4);
+        if (any_done && p.last_h1) {                                                            // :819-821
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if ((dn4 >> (8 * e)) & 1u) { p.last_h1[4 * g + e] = h1[e]; p.last_h2[4 * g + e] = h2[e]; }
+        }
+        if (obs_out) {
+            st4(obs_out, g, h1);
+            st4(obs_out + n, g, h2);
+            st4(obs_out + 2 * n, g, r);
+            if (integ) st4(obs_out + 3 * n, g, I);
+        }
+    }
+}
+
+// every array the vectorised kernels touch must be 16-byte aligned (4 envs per element); n % 4 == 0 keeps obs_out rows aligned
+static bool aligned16(std::initializer_list<const void *> ptrs) {
+    for (const void *q : ptrs)
+        if (q && ((uintptr_t)q & 15)) return false;
+    return true;
 }
 
 template <typename T>
@@ -132,9 +258,24 @@ static int wt_step_impl(const pime_wt_config *cfg, int64_t n, const pime_wt_stat
     PIME_REQUIRE((noise1 == nullptr) == (noise2 == nullptr), "noise1/noise2 must both be given or both be NULL");
     if (int rc = require_device()) return rc;
     if (n == 0) return PIME_OK;
-    wt_step_kernel<T><<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(make_wt_const<T>(*cfg), n, wt_ptrs<T>(st), action,
-                                                                               noise1, noise2, seed, env_offset, tick, obs_out,
-                                                                               reward, done);
+    int64_t i_begin = 0;
+    if constexpr (sizeof(T) == 4) {   // float: 4 envs per thread where layout and alignment allow, scalar kernel for the tail
+        const bool vec_ok = cfg->obs_mode != PIME_WT_OBS_STACKING && n >= kVec && (obs_out == nullptr || n % kVec == 0) &&
+                            aligned16({st->h1, st->h2, st->r, st->I, st->a1, st->a2, st->Kp, st->t, st->ep_return, action, noise1,
+                                       noise2, obs_out, reward}) && ((uintptr_t)done & 3) == 0;
+        if (vec_ok) {
+            const int64_t groups = n / kVec;
+            wt_step_vec4_kernel<<<grid_for(groups, kVecBlock, 32), kVecBlock, 0, (cudaStream_t)stream>>>(
+                make_wt_const<float>(*cfg), groups, n, wt_ptrs<float>(st), (const float *)action, (const float *)noise1,
+                (const float *)noise2, seed, env_offset, tick, (float *)obs_out, (float *)reward, done);
+            PIME_LAUNCH_CHECK();
+            i_begin = groups * kVec;
+            if (i_begin == n) return PIME_OK;
+        }
+    }
+    wt_step_kernel<T><<<grid_for(n - i_begin, kBlock), kBlock, 0, (cudaStream_t)stream>>>(make_wt_const<T>(*cfg), i_begin, n,
+                                                                                        wt_ptrs<T>(st), action, noise1, noise2, seed,
+                                                                                        env_offset, tick, obs_out, reward, done);
     PIME_LAUNCH_CHECK();
     return PIME_OK;
 }
@@ -153,16 +294,17 @@ static int wt_reset_impl(const pime_wt_config *cfg, int64_t n, const pime_wt_sta
 
 // ---------------------------------------------------------------------------------------------- pH
 template <typename T> struct PhPtrs {
-    T *x, *y, *r, *I, *A, *B, *C, *qww, *qc, *ep_return, *last_x;
+    double *x, *A, *B, *last_x;   // fp64 in both flavours (plants.cuh)
+    T *y, *r, *I, *C, *qww, *qc, *ep_return;
     int32_t *t;
     uint32_t *episode;
 };
 
 template <typename T> static PhPtrs<T> ph_ptrs(const pime_ph_state *s) {
     PhPtrs<T> p;
-    p.x = (T *)s->x; p.y = (T *)s->y; p.r = (T *)s->r; p.I = (T *)s->I;
-    p.A = (T *)s->A; p.B = (T *)s->B; p.C = (T *)s->C; p.qww = (T *)s->qww_V; p.qc = (T *)s->qc_V;
-    p.ep_return = (T *)s->ep_return; p.last_x = (T *)s->last_x; p.t = s->t; p.episode = s->episode;
+    p.x = (double *)s->x; p.y = (T *)s->y; p.r = (T *)s->r; p.I = (T *)s->I;
+    p.A = (double *)s->A; p.B = (double *)s->B; p.C = (T *)s->C; p.qww = (T *)s->qww_V; p.qc = (T *)s->qc_V;
+    p.ep_return = (T *)s->ep_return; p.last_x = (double *)s->last_x; p.t = s->t; p.episode = s->episode;
     return p;
 }
 
@@ -211,7 +353,7 @@ __global__ void __launch_bounds__(kBlock) ph_reset_kernel(PhConst<T> c, const T 
         uint32_t ep = p.episode[i];
         double u[6];
         reset_uniforms(seed, env_offset + (uint64_t)i, ep, u);
-        bool ok = ph_reset(c, table, e, qww, qc, u, resample != 0, c.from_last ? p.last_x[i] : nan_of<T>());
+        bool ok = ph_reset(c, table, e, qww, qc, u, resample != 0, c.from_last ? p.last_x[i] : nan_of<double>());
         if (!ok && status) atomicMin(status, (int32_t)PIME_ERANGE);
         p.episode[i] = ep + 1;
         p.qww[i] = qww; p.qc[i] = qc;
@@ -225,9 +367,10 @@ __global__ void __launch_bounds__(kBlock) ph_reset_kernel(PhConst<T> c, const T 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kBlock) ph_update_system_kernel(T sample_t, int64_t n, PhPtrs<T> p) {
+__global__ void __launch_bounds__(kBlock) ph_update_system_kernel(double sample_t, int64_t n, PhPtrs<T> p) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        T A, B, C;
+        double A, B;
+        T C;
         ph_update_system<T>(sample_t, p.qww[i], p.qc[i], A, B, C);
         p.A[i] = A; p.B[i] = B; p.C[i] = C;
     }
@@ -311,7 +454,7 @@ template <typename T> static int ph_update_impl(const pime_ph_config *cfg, int64
     if (int rc = check_ph(cfg, n, st)) return rc;
     if (int rc = require_device()) return rc;
     if (n == 0) return PIME_OK;
-    ph_update_system_kernel<T><<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>((T)cfg->sample_t, n, ph_ptrs<T>(st));
+    ph_update_system_kernel<T><<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(cfg->sample_t, n, ph_ptrs<T>(st));
     PIME_LAUNCH_CHECK();
     return PIME_OK;
 }

@@ -16,8 +16,8 @@ Where the work happens:
   * explore_env on a pime_b200 env (any ``num_envs``): ONE fused CUDA launch per episode batch
     (plant + prior + observation + tcgen05 actor + replay rows), the replay stays in HBM, time-major [T, n, .];
   * update_net: critic values of the whole buffer by the tcgen05 forward kernel, GAE / reward-to-go by the per-env
-    scan kernel; the minibatch surrogate / SmoothL1 step itself is torch autograd on the GPU (cuBLAS GEMMs) -- the
-    hand-written fused learner is the next row of SURVEY 8f and is NOT claimed here;
+    scan kernel; the minibatch surrogate / SmoothL1 / Adam step is pime_ppo_step (csrc/learner.cu, two hand-written
+    launches) whenever every parameter is trained; the frozen_* variants keep the torch autograd step;
   * torch.distributed (NCCL): replay stays sharded by env, gradients are averaged with one flat all-reduce per
     minibatch, the advantage normalisation uses global moments.
 Foreign gym envs (anything without a ``vec``) run the reference's sequential loop through select_action.
@@ -433,6 +433,14 @@ class AgentPPO:
     def frozen_transfer(self):
         self.cri.frozen_transfer()
         self.act.frozen_transfer()
+        self._invalidate_learner()
+
+    def _invalidate_learner(self):
+        """The recorded CUDA graph bakes in which parameters are trained and the fused learner keeps its own Adam moments:
+        both are dropped whenever the set of trained parameters changes (the moments restart from zero, as they would for
+        the parameters torch.optim.Adam has not seen a gradient of)."""
+        self._graph = None
+        self._fused = None
 
     # ---- kernel images of the networks
     def _pack(self, which):
@@ -631,7 +639,9 @@ class AgentPPO:
         """One PPO minibatch (index draw, gather, forward, backward, Adam) recorded ONCE into a CUDA graph and replayed:
         the reference's configurations (batch 128-512) are launch-latency bound (~60 small kernels per minibatch).
         The graph reads static copies of the buffer tensors; it is re-recorded when a shape changes."""
-        key = (buf_len, batch_size, self.graph_steps, tuple(t.shape for t in data))
+        trainable = tuple(p.requires_grad for grp in self.optimizer.param_groups for p in grp["params"])
+        key = (buf_len, batch_size, self.graph_steps, tuple(t.shape for t in data), trainable, float(self.ratio_clip),
+               float(self.lambda_entropy), tuple(float(grp["lr"]) for grp in self.optimizer.param_groups))
         if self._graph is None or self._graph["key"] != key:
             static = tuple(torch.empty_like(t) for t in data)
             out = torch.zeros(8, device=self.device)
@@ -689,6 +699,7 @@ class Residual:
 
     def fix_K(self):
         self.act.priorK.requires_grad = False
+        self._invalidate_learner()
 
 
 class AgentResidualPPO(AgentPPO, Residual):
@@ -712,6 +723,7 @@ class AgentResidualIntegratorModularPPO(AgentResidualPPO):
     def frozen_integrator(self):
         self.act.frozen_integrator()
         self.cri.frozen_transfer()
+        self._invalidate_learner()
 
 
 MODELS = {"ppo": AgentPPO, "residualppo": AgentResidualPPO, "residualintegratormodularppo": AgentResidualIntegratorModularPPO}
@@ -784,6 +796,9 @@ class PreprocessEnv:
         return np.asarray(state).astype(self.data_type), reward, done, info
 
     def __getattr__(self, name):  # delegate everything else (if_reset_all, K, n_integrator, ...)
+        # copy / pickle probe dunders (__deepcopy__, __setstate__, ...) on an instance whose __dict__ is still empty
+        if name.startswith("__") or "env" not in self.__dict__:
+            raise AttributeError(name)
         return getattr(self.__dict__["env"], name)
 
 
@@ -818,6 +833,7 @@ def evaluate_batched(env, agent, episodes: Optional[int] = None):
         vec.ep_return.zero_()
         vec.rollout(T, np.asarray(agent.priorK, dtype=np.float64).reshape(-1), actor=agent._pack("act"), deterministic=True)
         out += [(float(r), T) for r in vec.ep_return.cpu().numpy()]
+    vec.check_status()
     return out[:episodes] if episodes else out
 
 

@@ -91,7 +91,7 @@ class ActorPack:
 
 # ------------------------------------------------------------------------------------------------------ shared rollout glue
 def _rollout_args(env, T, actor, priorK, deterministic, auto_reset, reward_scale, gamma, eps, pnoise, replay, want_actions,
-                  stats, keep, a_std_log=None):
+                  stats, keep, a_std_log=None, keep_params=False):
     n, S = env.n, env.state_dim
     a = L.RolloutArgs()
     a.a_std_log = -0.5 if a_std_log is None else float(a_std_log)   # net_residual.py:162 initial value
@@ -132,15 +132,15 @@ def _rollout_args(env, T, actor, priorK, deterministic, auto_reset, reward_scale
         stats = torch.zeros(8, dtype=torch.float64, device=env.device)
     out["stats"] = stats
     a.stats = L.ptr(stats)
-    env.status.zero_()
-    a.status = L.ptr(env.status)
+    a.status = L.ptr(env.status)   # device fault flag: accumulated (atomicMin) until check_status() reads and clears it
+    a.keep_params = int(keep_params)
     return a, out
 
 
 class _VecBase:
-    def _alloc(self, names, n):
+    def _alloc(self, names, n, f64=()):
         for k in names:
-            setattr(self, k, torch.zeros(n, dtype=self.dtype, device=self.device))
+            setattr(self, k, torch.zeros(n, dtype=torch.float64 if k in f64 else self.dtype, device=self.device))
         self.t = torch.full((n,), -1, dtype=torch.int32, device=self.device)   # -1: "Please reset the env first"
         self.episode = torch.zeros(n, dtype=torch.int32, device=self.device)
         self.ep_return = torch.zeros(n, dtype=self.dtype, device=self.device)
@@ -235,12 +235,13 @@ class WaterTankVec(_VecBase):
 
     def rollout(self, T: int, priorK, actor: Optional[ActorPack] = None, deterministic=False, auto_reset=False,
                 reward_scale=1.0, gamma=0.99, eps=None, pnoise=None, replay=None, want_actions=False, stats=None,
-                a_std_log=None):
+                a_std_log=None, resample_params=True):
         """T fused steps (plant + prior + obs + actor) in one launch; see pime_wt_rollout_* in the header.
-        eps=None draws the exploration noise in the kernel (Philox); pass a zero tensor for a noise-free policy."""
+        eps=None draws the exploration noise in the kernel (Philox); pass a zero tensor for a noise-free policy.
+        resample_params=False: the in-kernel auto-reset keeps (a1, a2, Kp) like reset_r() (if_reset_all=False)."""
         keep = []
         a, out = _rollout_args(self, T, actor, priorK, deterministic, auto_reset, reward_scale, gamma, eps, pnoise, replay,
-                               want_actions, stats, keep, a_std_log)
+                               want_actions, stats, keep, a_std_log, keep_params=not resample_params)
         L.check(_fn("pime_wt_rollout", self.dtype)(C.byref(self.cfg), C.c_int64(self.n), C.byref(self._st), C.byref(a),
                                                    L.stream_ptr()))
         self.tick += T
@@ -255,7 +256,7 @@ class WaterTankVec(_VecBase):
         keep = []
         a, out = _rollout_args(self, T, actor, priorK, deterministic, kw.pop("auto_reset", False), kw.pop("reward_scale", 1.0),
                                kw.pop("gamma", 0.99), None, None, kw.pop("replay", None), False, kw.pop("stats", None), keep,
-                               kw.pop("a_std_log", None))
+                               kw.pop("a_std_log", None), keep_params=not kw.pop("resample_params", True))
         assert not kw, f"unknown arguments {list(kw)}"
         hs = L.WtState(**{k: L.ptr(host_state.get(k)) for k in ("h1", "h2", "r", "I", "a1", "a2", "Kp", "t", "episode")})
         if ep_return_host is None:
@@ -310,11 +311,12 @@ class PHVec(_VecBase):
                                **cfg)
         self.state_dim = 2 if integrator == "none" else 3
         self.integrator = integrator
-        self._alloc(["x", "y", "r", "I", "A", "B", "C", "qww_V", "qc_V"], self.n)
+        # x, A, B (and last_x) are fp64 in both flavours: the titration index rint(C x 1e5) must not depend on the dtype
+        self._alloc(["x", "y", "r", "I", "A", "B", "C", "qww_V", "qc_V"], self.n, f64=("x", "A", "B"))
         t64, t32 = ph_table(self.cfg, self.device)
         self.table = t64 if dtype == torch.float64 else t32
         # state at the last time-limit step (ph.py:102, :345-346); NaN = None
-        self.last_x = (torch.full((self.n,), float("nan"), dtype=dtype, device=self.device) if reset_from_last_state else None)
+        self.last_x = (torch.full((self.n,), float("nan"), dtype=torch.float64, device=self.device) if reset_from_last_state else None)
         self._st = L.PhState(x=L.ptr(self.x), y=L.ptr(self.y), r=L.ptr(self.r), I=L.ptr(self.I), A=L.ptr(self.A),
                              B=L.ptr(self.B), C=L.ptr(self.C), qww_V=L.ptr(self.qww_V), qc_V=L.ptr(self.qc_V),
                              t=L.ptr(self.t), episode=L.ptr(self.episode), ep_return=L.ptr(self.ep_return),
@@ -332,7 +334,6 @@ class PHVec(_VecBase):
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
             obs.copy_(self.observe())
-        self.status.zero_()
         L.check(_fn("pime_ph_reset", self.dtype)(C.byref(self.cfg), L.ptr(self.table), C.c_int64(self.n), C.byref(self._st),
                                                  C.c_uint64(self.seed), C.c_uint64(self.env_offset),
                                                  C.c_int(int(resample_params)), L.ptr(mask), L.ptr(obs), L.ptr(self.status),
@@ -367,10 +368,11 @@ class PHVec(_VecBase):
         return out
 
     def rollout(self, T: int, priorK, actor: Optional[ActorPack] = None, deterministic=False, auto_reset=False,
-                reward_scale=1.0, gamma=0.99, eps=None, replay=None, want_actions=False, stats=None, a_std_log=None):
+                reward_scale=1.0, gamma=0.99, eps=None, replay=None, want_actions=False, stats=None, a_std_log=None,
+                resample_params=True):
         keep = []
         a, out = _rollout_args(self, T, actor, priorK, deterministic, auto_reset, reward_scale, gamma, eps, None, replay,
-                               want_actions, stats, keep, a_std_log)
+                               want_actions, stats, keep, a_std_log, keep_params=not resample_params)
         L.check(_fn("pime_ph_rollout", self.dtype)(C.byref(self.cfg), L.ptr(self.table), C.c_int64(self.n), C.byref(self._st),
                                                    C.byref(a), L.stream_ptr()))
         self.tick += T

@@ -41,6 +41,6 @@ def load_wt(env, d):
 def load_ph(env, d):
     for k in ("x", "y", "r", "I", "A", "B", "C", "qww_V", "qc_V"):
         if k in d:
-            getattr(env, k).copy_(dev(d[k], env.dtype))
+            getattr(env, k).copy_(dev(d[k], getattr(env, k).dtype))   # x, A, B are fp64 in both flavours
     env.t.copy_(dev(d["t"], torch.int32))
     env.ep_return.zero_()
