@@ -65,6 +65,7 @@ def parse():
     p.add_argument("--net-dim", type=int, default=0)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-aux", action="store_true", help="skip the stand-alone step-kernel roofline measurements")
+    p.add_argument("--no-extra", action="store_true", help="skip the configs[3] / configs[4] measurements that follow the headline")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--batch-size", type=int, default=1 << 17, help="train workload: PPO minibatch rows")
     p.add_argument("--repeat-times", type=int, default=2, help="train workload: PPO epochs over the buffer")
@@ -244,6 +245,45 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+
+def time_e2e(step_fn, steps, world, units_per_step, barrier, dist):
+    """Wall-clock of `steps` host-driven calls (each ends with a device->host read), max over ranks."""
+    import torch
+    step_fn()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_fn()
+    barrier()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"value": world * units_per_step * steps / float(t.item()), "unit": UNIT, "steps": steps}
+
+
+def ph_e2e(env, actor, T, K, bs, bo, stats, steps, world, barrier, dist):
+    """configs[3] end to end: PHVec.rollout_host -> pime_ph_rollout_host_f32 with pinned host state."""
+    import torch
+    n = env.n
+    host = {k: getattr(env, k).detach().cpu().pin_memory() for k in env.HOST_FIELDS if k not in ("t",)}
+    host["t"] = torch.zeros(n, dtype=torch.int32).pin_memory()
+    ret_host = torch.empty(n, dtype=torch.float32).pin_memory()
+    flat_host = actor.flat.detach().cpu().pin_memory()
+    h2d = sum(v.numel() * v.element_size() for v in host.values()) + flat_host.numel() * 4
+    d2h = n * 4 + n * (8 + 4 + 4 + 4) + 64
+
+    def step():
+        actor.flat.copy_(flat_host, non_blocking=True)
+        actor.update_from_flat()
+        out = env.rollout_host(host, T, -K, actor=actor, ep_return_host=ret_host, replay=(bs, bo), stats=stats)
+        return float(out["stats"].cpu()[0])
+
+    e = time_e2e(step, steps, world, n * T, barrier, dist)
+    e.update({"h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+              "api": "PHVec.rollout_host -> pime_ph_rollout_host_f32 (pinned host state in, ep_return + final state out)"})
+    return e
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -312,7 +352,8 @@ def run_b200(args):
     st = stats.cpu().numpy()
     env.check_status()
 
-    # ---- e2e: the host-buffer API call (pinned host state in, ep_return out), H2D/D2H inside the timed region
+    # ---- e2e: the host-buffer API call (pinned host state in, ep_return out), H2D/D2H inside the timed region; timed over
+    # args.steps calls directly after the device-timed loop (same clocks / thermal state, so the two numbers compare)
     e2e = None
     if is_wt:
         host = {k: getattr(env, k).detach().cpu().pin_memory() for k in ("h1", "h2", "r", "I", "a1", "a2", "Kp")}
@@ -329,20 +370,11 @@ def run_b200(args):
             out = env.rollout_host(host, T, -K, actor=actor, ep_return_host=ret_host, replay=(bs, bo), stats=stats)
             return float(out["stats"].cpu()[0])                       # D2H of the step's metric (sum of episode returns)
 
-        e2e_steps = max(2, min(args.steps, 3))
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n * T * e2e_steps / float(e2e_t.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h),
-               "api": "WaterTankVec.rollout_host -> pime_wt_rollout_host_f32 (pinned host state in, ep_return + final state out)"}
+        e2e = time_e2e(e2e_step, args.steps, world, n * T, barrier, dist)
+        e2e.update({"h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "WaterTankVec.rollout_host -> pime_wt_rollout_host_f32 (pinned host state in, ep_return + final state out)"})
+    elif args.workload == "ph":
+        e2e = ph_e2e(env, actor, T, K, bs, bo, stats, args.steps, world, barrier, dist)
 
     kname = f"rollout_kernel<{'PhGlue' if args.workload == 'ph' else 'WtGlue'}<float>, {kind}, {H}>"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -360,6 +392,20 @@ def run_b200(args):
             "episode_stats": {"mean_return": st[0] / max(st[2], 1), "episodes": st[2]}}
     if e2e:
         line["e2e"] = e2e
+
+    extra = {}
+    if is_wt and not args.no_extra and not (args.envs or args.T or args.net_dim):
+        # configs[3] and configs[4] of BASELINE.json, measured in the same invocation (outside the timed region of the headline)
+        # so that the driver's 1/2/4/8-GPU runs record them too
+        del bs, bo
+        if e2e is not None:
+            del host, ret_host
+        torch.cuda.empty_cache()
+        extra["config4"] = extra_config4(V, world, rank, dist, barrier, pk)
+        torch.cuda.empty_cache()
+        extra["config5"] = extra_config5(world, rank, dist, barrier)
+    if extra:
+        line["extra"] = extra
 
     if rank == 0:
         flops = FLOPS_PER_STEP.get((kind, H, S))
@@ -385,6 +431,99 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+
+def extra_config4(V, world, rank, dist, barrier, pk, steps=5, warmup=2):
+    """BASELINE configs[3]: pH ensemble sweep, 2^23 envs in total sharded contiguously over the ranks (strong scaling),
+    T = 50, Modular-128, in-kernel auto-reset with ensemble resampling, replay rows written."""
+    import torch
+    w = dict(WORKLOADS["ph"])
+    total = w["envs"]
+    n, T, H, S = max(1, total // world), w["T"], w["H"], w["S"]
+    K = np.array(w["K"])
+    sd = actor_state_dict(H, S)
+    actor = V.ActorPack("modular", S, H, 1).update(sd)
+    env = V.PHVec(n, dtype=torch.float32, seed=0, env_offset=rank * n)
+    env.reset()
+    bs = torch.empty((T, n, S), dtype=torch.float32, device="cuda")
+    bo = torch.empty((T, n, 4), dtype=torch.float32, device="cuda")
+    stats = torch.zeros(8, dtype=torch.float64, device="cuda")
+
+    def step():
+        stats.zero_()
+        env.rollout(T, -K, actor=actor, auto_reset=True, replay=(bs, bo), stats=stats, gamma=0.99)
+        if world > 1:
+            dist.all_reduce(stats)
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    env.check_status()
+    out = {"metric": METRIC, "value": world * n * T / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "ms_per_step": ms, "steps": steps,
+           "scaling": "strong", "workload": w["name"], "envs_total": n * world, "envs_per_gpu": n, "T": T,
+           "actor": "ResidualIntegratorModularPPO-" + str(H), "dtype": "x, A, B, table index: f64; rest f32; hidden layers f16 operands",
+           "tensor_tflops": world * n * T * FLOPS_PER_STEP[("modular", H, S)] / (ms * 1e-3) / 1e12}
+    out["e2e"] = ph_e2e(env, actor, T, K, bs, bo, stats, 3, world, barrier, dist)
+    return out
+
+
+def extra_config5(world, rank, dist, barrier, n=1 << 13, batch=4096, repeat=2, iters=2):
+    """BASELINE configs[4]: full residual PPO training -- explore (one fused launch into the GPU-resident replay), critic
+    values + GAE kernels, repeat * T * n / batch minibatch steps with the gradient all-reduce when world > 1."""
+    import torch
+    import pime_b200.gym_api as G
+    import pime_b200.rl as R
+    w = WORKLOADS["train"]
+    T, H = w["T"], w["H"]
+    env = R.PreprocessEnv(G.make(w["env"], num_envs=n, dtype=torch.float32))
+    env.env.vec.env_offset = rank * n
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    agent = R.AgentResidualIntegratorModularPPO()
+    agent.init(H, env.state_dim, env.action_dim, env.n_integrator)
+    agent.init_residual({"init_K": env.K.reshape(-1, 1)})
+    buf = R.ReplayBuffer(n * T, env.state_dim, 1, True, False, True, num_envs=n)
+    t_roll = t_upd = 0.0
+
+    def step():
+        nonlocal t_roll, t_upd
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        steps = agent.explore_env(env, buf, n * T, 1.0, 0.99)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        agent.update_net(buf, steps, batch, repeat)
+        torch.cuda.synchronize()
+        t_roll += t1 - t0
+        t_upd += time.perf_counter() - t1
+
+    step()
+    barrier()
+    t_roll = t_upd = 0.0
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    return {"metric": "PPO training transitions/sec (explore + update)", "value": world * n * T * iters / float(dt.item()),
+            "unit": "env-steps/s", "n_gpus": world, "scaling": "weak", "workload": w["name"], "envs_per_gpu": n, "T": T,
+            "actor": "ResidualIntegratorModularPPO-" + str(H), "batch_size": batch, "repeat_times": repeat,
+            "minibatches_per_iteration": int(repeat * n * T / batch), "iterations": iters,
+            "learner": agent.learner_path, "dtype": "f32 learner; rollout as the headline",
+            "rollout_share": t_roll / max(t_roll + t_upd, 1e-9), "rollout_ms": 1e3 * t_roll / iters, "update_ms": 1e3 * t_upd / iters}
 
 
 def aux_step_rooflines(V, pk):
@@ -496,9 +635,7 @@ def run_train(args):
                           "config": {"workload": w["name"], "envs_per_gpu": n, "T": T, "actor": w["actor"], "batch_size": args.batch_size,
                                      "repeat_times": args.repeat_times,
                                      "minibatches_per_step": int(args.repeat_times * n * T / args.batch_size),
-                                     "learner": "values + GAE: CUDA kernels; minibatch step: "
-                                                + ("pime_ppo_step (two hand-written launches, fp32, fused Adam)" if agent._fused is not None
-                                                   else "torch autograd (cuBLAS, " + ("TF32" if args.tf32 else "fp32") + ")")},
+                                     "learner": "values + GAE: CUDA kernels; minibatch step: " + str(agent.learner_path)},
                           "rollout_share": t_roll / (t_roll + t_upd), "rollout_ms_per_step": 1e3 * t_roll / args.steps,
                           "update_ms_per_step": 1e3 * t_upd / args.steps}), flush=True)
     if world > 1:

@@ -101,6 +101,7 @@ def main():
     kargs = Arguments(if_on_policy=IF_ONPOLICY[algo])
     kargs.env = PreprocessEnv(env)
     kargs.env_eval = PreprocessEnv(make_env(args, max(args.eval_times2, 1)))
+    kargs.env_eval.env.vec.seed = args.seed + 104729      # distinct Philox streams: evaluation must not replay the training draws
     kargs.agent = MODELS[algo]()
     kargs.agent.learning_rate = args.learning_rate
     kargs.agent.lambda_entropy, kargs.agent.ratio_clip, kargs.agent.lambda_gae_adv = args.lambda_entropy, args.ratio_clip, args.lambda_gae_adv
@@ -127,7 +128,10 @@ def main():
     if "Stacking" not in args.env:
         save_staircase(kargs.env, agent, final)
         if args.robust_test and "NonLinearWaterTank" in args.env:          # train.py:203-205
-            res, p = scenarios.robust_sweep(env.K, actor=agent._pack("act"), obs_mode=env._obs_mode, max_step=500)
+            cfg = env._cfg_kwargs()      # the sweep runs under the training env's reward type / noise setting
+            cfg.pop("max_step", None)
+            res, p = scenarios.robust_sweep(env.K, actor=agent._pack("act"), obs_mode=env._obs_mode, max_step=500,
+                                            dtype=env._dtype, seed=args.seed + 7919, **cfg)
             np.savez_compressed(os.path.join(kargs.cwd, "robust_test.npz"), params=p, **{k: v.cpu().numpy() for k, v in res.items() if v is not None})
     with open(os.path.join(kargs.cwd, "args.txt"), "w") as f:
         f.write(str(args))

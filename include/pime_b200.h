@@ -284,6 +284,10 @@ int pime_reduce_episode_stats_f64(int64_t n, const double *ep_return, double *st
  * ------------------------------------------------------------------------------------------------------- */
 int pime_wt_rollout_host_f32(const pime_wt_config *cfg, int64_t n, const pime_wt_state *st_host, const pime_wt_state *st_dev,
                              const pime_rollout_args *args, float *ep_return_host, void *stream);
+/* pH flavour: st_host holds x, A, B as double[n] and y, r, I, C, qww_V, qc_V as float[n] (t, episode int32 / uint32);
+ * x, y, r, I of the final state are copied back.  `table` is the DEVICE table of pime_ph_table_build. */
+int pime_ph_rollout_host_f32(const pime_ph_config *cfg, const float *table, int64_t n, const pime_ph_state *st_host,
+                             const pime_ph_state *st_dev, const pime_rollout_args *args, float *ep_return_host, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * PPO learner: one minibatch step of AgentPPO.update_net (elegantrl/agent.py:635-658) on the GPU-resident replay
@@ -326,6 +330,12 @@ int pime_ppo_theta_layout(const pime_actor_config *actor, int64_t *out3); /* cri
 int64_t pime_ppo_work_floats(const pime_actor_config *actor, int32_t batch);
 int pime_ppo_transpose(const pime_actor_config *actor, const float *theta, float *theta_t, void *stream);
 int pime_ppo_step(const pime_ppo_args *args, void *stream);
+/* Data-parallel training (BASELINE configs[4]): every rank runs pime_ppo_step with grad_out set (the gradient of obj_united
+ * over ITS minibatch rows, flat, theta's layout), the caller all-reduces that buffer (NCCL), then this entry applies
+ * torch.optim.Adam's arithmetic to theta / theta_t / the moments with grad * scale (scale = 1 / world size for the mean).
+ * It must follow the pime_ppo_step of the same step on the same stream: the step count and the bias corrections are
+ * the ones that call left in `state`. */
+int pime_ppo_apply_grad(const pime_ppo_args *args, const float *grad, float scale, void *stream);
 
 /* misc */
 int pime_abi_version(void);

@@ -81,8 +81,8 @@ SYMBOLS = [
     "pime_actor_param_count", "pime_actor_pack_bytes", "pime_actor_block_list", "pime_actor_pack", "pime_actor_forward",
     "pime_wt_rollout_f32", "pime_wt_rollout_f64", "pime_ph_rollout_f32", "pime_ph_rollout_f64",
     "pime_gae_scan", "pime_reduce_episode_stats_f32", "pime_reduce_episode_stats_f64",
-    "pime_ppo_theta_count", "pime_ppo_theta_layout", "pime_ppo_work_floats", "pime_ppo_transpose", "pime_ppo_step",
-    "pime_wt_rollout_host_f32", "pime_abi_version", "pime_last_error", "pime_device_info", "pime_philox_probe",
+    "pime_ppo_theta_count", "pime_ppo_theta_layout", "pime_ppo_work_floats", "pime_ppo_transpose", "pime_ppo_step", "pime_ppo_apply_grad",
+    "pime_wt_rollout_host_f32", "pime_ph_rollout_host_f32", "pime_abi_version", "pime_last_error", "pime_device_info", "pime_philox_probe",
 ]
 
 _lib = None

@@ -706,6 +706,30 @@ __global__ void __launch_bounds__(kThreads) ppo_wgrad_kernel(const StepParams p)
     }
 }
 
+
+// Adam on a flat gradient in theta's layout (the distributed path: pime_ppo_step(grad_out) -> all-reduce -> this).  One
+// thread per parameter of every layer (grid.y = layer); the transposed copy is kept in step.  adam_c was written by the
+// rows kernel of the same step (adam_prepare), so the bias corrections belong to the step whose gradient this is.
+__global__ void __launch_bounds__(kThreads) ppo_adam_kernel(const StepParams p, const float *__restrict__ grad, float scale) {
+    const LayerDesc L = p.layer[blockIdx.y];
+    const AdamCoef c = adam_coef(p);
+    const int nw = L.N * L.K, total = nw + L.N;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x) {
+        int idx, idx_t;
+        if (j < nw) { const int n = j / L.K, k = j % L.K; idx = L.w_off + j; idx_t = L.w_off + k * L.N + n; }
+        else { idx = idx_t = L.b_off + (j - nw); }
+        float m = p.m[idx], v = p.v[idx];
+        const float th = adam_update(c, grad[idx] * scale, p.theta[idx], m, v);
+        p.m[idx] = m; p.v[idx] = v; p.theta[idx] = th; p.theta_t[idx_t] = th;
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {   // a_std_log
+        const int idx = p.n_theta - 1;
+        float m = p.m[idx], v = p.v[idx];
+        const float th = adam_update(c, grad[idx] * scale, p.theta[idx], m, v);
+        p.m[idx] = m; p.v[idx] = v; p.theta[idx] = th; p.theta_t[idx] = th;
+    }
+}
+
 __global__ void ppo_transpose_kernel(StepParams p) {
     for (int li = 0; li < p.n_layers; ++li) {
         const LayerDesc L = p.layer[li];
@@ -847,6 +871,19 @@ int pime_ppo_transpose(const pime_actor_config *actor, const float *theta, float
     if (int rc = ppo::fill_params(&a, p)) return rc;
     if (int rc = require_device()) return rc;
     ppo::ppo_transpose_kernel<<<kNumSMs, 256, 0, (cudaStream_t)stream>>>(p);
+    PIME_LAUNCH_CHECK();
+    return PIME_OK;
+}
+
+int pime_ppo_apply_grad(const pime_ppo_args *a, const float *grad, float scale, void *stream) {
+    ppo::StepParams p;
+    if (int rc = ppo::fill_params(a, p)) return rc;
+    PIME_REQUIRE(a->theta && a->theta_t && a->adam_m && a->adam_v && a->state && grad, "null theta / theta_t / moments / state / grad");
+    if (int rc = require_device()) return rc;
+    p.lr = a->lr; p.beta1 = a->beta1; p.beta2 = a->beta2; p.eps = a->eps;
+    p.step_dev = (int *)a->state;
+    p.adam_c = (float *)a->state + 8;
+    ppo::ppo_adam_kernel<<<dim3(32, p.n_layers), ppo::kThreads, 0, (cudaStream_t)stream>>>(p, grad, scale);
     PIME_LAUNCH_CHECK();
     return PIME_OK;
 }

@@ -62,6 +62,17 @@ def _f(x):
     return float(np.asarray(x, dtype=np.float64).reshape(-1)[0])
 
 
+def _mirror(name):
+    """Host-side view of one per-env device array: read -> python scalar (num_envs = 1) or numpy array; write -> broadcast."""
+    def get(self):
+        return self._scalar(getattr(self.vec, name))
+
+    def put(self, v):
+        t = getattr(self.vec, name)
+        t.copy_(torch.as_tensor(v, dtype=t.dtype, device=t.device).expand_as(t))
+    return property(get, put)
+
+
 class _DeviceEnv(_EnvBase):
     """Shared plumbing: a *Vec object of num_envs envs plus host-side mirrors of the reference attributes."""
 
@@ -210,18 +221,14 @@ class NonLinearWaterTankChangingParamUniformGoal(_DeviceEnv):
 
     # ---- test / inspection API (nonlinear_watertank.py:205-212, :755-759)
     def set_state(self, h1, h2):
+        """nonlinear_watertank.py:205-208.  The stacking variant inherits it unchanged: the frame history is NOT touched
+        (frames change only in reset() and step(), :1145-1146,:1183-1184), so the returned observation is the old history."""
         self._reset_done = True
         self.vec.set_state(h1, h2)
-        if self.vec.frames is not None:
-            k = self.num_stack
-            self.vec.frames[3 * (k - 1)].copy_(self.vec.h1)
-            self.vec.frames[3 * (k - 1) + 1].copy_(self.vec.h2)
         return self._get_observe()
 
     def set_r(self, r):
         self.vec.set_r(r)
-        if self.vec.frames is not None:
-            self.vec.frames[3 * (self.num_stack - 1) + 2].copy_(self.vec.r)
         return self._get_observe()
 
     def get_P_action(self, state):
@@ -241,13 +248,21 @@ class NonLinearWaterTankChangingParamUniformGoal(_DeviceEnv):
     def close(self):
         self._reset_done = False
 
-    # host mirrors of the reference attributes
-    h1 = property(lambda self: self._scalar(self.vec.h1))
-    h2 = property(lambda self: self._scalar(self.vec.h2))
-    r = property(lambda self: self._scalar(self.vec.r))
-    a1 = property(lambda self: self._scalar(self.vec.a1))
-    a2 = property(lambda self: self._scalar(self.vec.a2))
-    Kp = property(lambda self: self._scalar(self.vec.Kp))
+    # host mirrors of the reference attributes; assignable like the plain attributes they mirror (utils/robust_test.py:12-37
+    # writes test_env.a1 / a2 / Kp / max_step / if_reset_all directly)
+    h1, h2, r = _mirror("h1"), _mirror("h2"), _mirror("r")
+    a1, a2, Kp = _mirror("a1"), _mirror("a2"), _mirror("Kp")
+
+    @property
+    def max_step(self):
+        return self._max_step
+
+    @max_step.setter
+    def max_step(self, v):
+        self._max_step = int(v)
+        if "vec" in self.__dict__:
+            self.vec.cfg.max_step = int(v)
+
     state = property(lambda self: self._get_observe())
     _episode_steps = property(lambda self: self._scalar(self.vec.t))
 

@@ -38,39 +38,34 @@ from . import vec as V
 
 
 # ====================================================================================================== logger
-class Logger:
-    """Minimal stand-in for the reference's (missing) elegantrl/logger.py: SB3-style record / dump, csv on disk."""
-
-    def __init__(self):
-        self.values, self.path, self.verbose = {}, None, 0
-        self.history = []
-
-    def configure(self, folder: Optional[str], verbose: int = 0):
-        self.path, self.verbose = folder, verbose
-        if folder:
-            os.makedirs(folder, exist_ok=True)
-
-    def record(self, key, value):
-        self.values[key] = float(value)
-
-    def dump(self, step=0):
-        row = dict(self.values, step=int(step))
-        self.history.append(row)
-        if self.path:
-            with open(os.path.join(self.path, "progress.csv"), "a") as f:
-                f.write(",".join(f"{k}={v}" for k, v in sorted(row.items())) + "\n")
-        if self.verbose:
-            print(" | ".join(f"{k} {v:.4g}" for k, v in sorted(row.items())))
-        self.values = {}
+from . import logger  # noqa: E402  (SB3-style module-level logger: the reference's elegantrl/logger.py is missing)
 
 
-logger = Logger()
+def get_latest_run_id(log_path: Optional[str] = None, log_name: str = "") -> int:
+    """Greatest N among the directories ``{log_path}/{log_name}_N`` (elegantrl/utils.py:10-24)."""
+    import glob
+    best = 0
+    for path in glob.glob(f"{log_path}/{log_name}_[0-9]*"):
+        head, _, ext = os.path.basename(path).rpartition("_")
+        if head == log_name and ext.isdigit():
+            best = max(best, int(ext))
+    return best
 
 
 def configure_logger(verbose=0, tensorboard_log=None, tb_log_name="", reset_num_timesteps=True):
-    """elegantrl/utils.py:26-47 (SB3-style); tensorboard is not available here, rows go to progress.csv."""
-    folder = os.path.join(tensorboard_log, tb_log_name) if tensorboard_log else None
-    logger.configure(folder, verbose)
+    """elegantrl/utils.py:26-47: outputs go to ``{tensorboard_log}/{tb_log_name}_{run id}`` as tensorboard events + csv
+    (+ stdout when verbose >= 1).  The reference only writes files when tensorboard is importable; the csv is written here
+    either way."""
+    if tensorboard_log is not None:
+        run = get_latest_run_id(tensorboard_log, tb_log_name)
+        if not reset_num_timesteps:
+            run -= 1
+        save_path = os.path.join(tensorboard_log, f"{tb_log_name}_{run + 1}")
+        logger.configure(save_path, (["stdout"] if verbose >= 1 else []) + ["tensorboard", "csv"])
+    elif verbose == 0:
+        logger.configure(format_strings=[""])
+    else:
+        logger.configure(format_strings=["stdout"])
     return logger
 
 
@@ -226,6 +221,7 @@ class FusedLearner:
         self.state = torch.zeros(1024, dtype=torch.int32, device=device)
         self.loss_ring = torch.zeros((self.RING, 4), dtype=torch.float32, device=device)
         self.work = None
+        self.grad = None        # distributed: flat gradient of this rank's minibatch, all-reduced before the Adam kernel
         self.steps = 0          # host mirror of the device step count
         self._args = None
         self._step_fn = V.L.lib().pime_ppo_step
@@ -233,8 +229,9 @@ class FusedLearner:
 
     @staticmethod
     def eligible(agent, batch_size):
-        """Everything trainable (the frozen_* / fix-K variants keep the autograd step), one action, single process."""
-        if _dist_on() or agent.act.kind not in ("plain", "modular") or not 2 <= batch_size <= agent.fused_max_batch:
+        """Everything trainable (the frozen_* variants keep the autograd step), one action.  Under torch.distributed the
+        step becomes rows + weight-gradient kernels -> flat all-reduce -> Adam kernel (pime_ppo_apply_grad)."""
+        if agent.act.kind not in ("plain", "modular") or not 2 <= batch_size <= agent.fused_max_batch:
             return False
         named = list(agent.act.named_parameters()) + list(agent.cri.named_parameters())
         return all(p.requires_grad or n == "priorK" for n, p in named) and agent.act.a_std_log.numel() == 1
@@ -289,8 +286,18 @@ class FusedLearner:
             self._args = (key, a, C.byref(a), data)
         a = self._args[1]
         a.idx = idx.data_ptr()
-        L.check(self._step_fn(self._args[2], C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        L.check(self._step_fn(self._args[2], stream))
+        if grad_out is not None and grad_out is self.grad:   # data parallel: mean gradient over the job, then Adam
+            torch.distributed.all_reduce(grad_out)
+            L.check(L.lib().pime_ppo_apply_grad(self._args[2], L.ptr(grad_out), C.c_float(1.0 / torch.distributed.get_world_size()),
+                                                stream))
         self.steps += 1
+
+    def dist_grad(self):
+        if self.grad is None:
+            self.grad = torch.zeros_like(self.theta)
+        return self.grad
 
     def losses(self, first, count):
         """Rows [first, first + count) of the loss ring -> [count, 4] (united, actor, critic, entropy)."""
@@ -399,6 +406,7 @@ class AgentPPO:
         self.use_fused_learner = True   # pime_ppo_step (two launches per minibatch) when FusedLearner.eligible
         self.fused_max_batch = 4096     # beyond it the cuBLAS autograd step is faster than the fp32 SIMT kernels
         self._fused = None
+        self.learner_path = None        # which minibatch step the last update_net ran (reported by bench.py)
 
     # ---- construction
     def _make_actor(self, net_dim, state_dim, action_dim, **kw):
@@ -579,6 +587,7 @@ class AgentPPO:
         if self.use_fused_learner and iters and FusedLearner.eligible(self, batch_size):
             return self._update_fused(data, buf_len, batch_size, iters, repeat_times)
 
+        self.learner_path = "torch autograd (cuBLAS, " + ("TF32" if torch.backends.cuda.matmul.allow_tf32 else "fp32") + ")"
         sums = torch.zeros(4, device=self.device)
         last = torch.zeros(4, device=self.device)
         use_graph = self.use_cuda_graph and iters >= 8 and batch_size <= self.graph_max_batch and not _dist_on()
@@ -620,10 +629,13 @@ class AgentPPO:
         f.load(self.act, self.cri)
         data = (data[0].contiguous(),) + tuple(t.reshape(-1).contiguous() for t in data[1:])   # [L, S], then four [L] columns
         first = f.steps
+        grad = f.dist_grad() if _dist_on() else None
         for _ in range(iters):
             idx = torch.randint(buf_len, size=(batch_size,), device=self.device)
-            f.step(data, idx, self)
+            f.step(data, idx, self, grad)
         f.store(self.act, self.cri)
+        self.learner_path = ("pime_ppo_step (rows + weight-gradient kernels, fp32" +
+                             (", NCCL all-reduce of the flat gradient, Adam kernel)" if grad is not None else ", Adam fused)"))
         f._args = None                      # do not keep the replay tensors alive between calls
         self._n_updates += int(repeat_times)
         keep = min(iters, f.RING - 1)
@@ -968,6 +980,10 @@ def train_and_evaluate(args):
     logger.dump(step=0)
     agent.state = env.reset()
     total_step = 0
+    if args.test_render is not None:                       # run.py:188-191: the self-designed evaluation at step 0
+        save_path = os.path.join(cwd, "step_0")
+        os.makedirs(save_path, exist_ok=True)
+        args.test_render(agent, save_path)
     while not ((args.if_allow_break and if_reach_goal) or total_step >= args.break_step or os.path.exists(f"{cwd}/stop")):
         steps = agent.explore_env(env, buffer, args.target_step, args.reward_scale, args.gamma)
         total_step += steps

@@ -61,8 +61,8 @@ def staircase(vec, policy: str, K, actor: Optional[V.ActorPack] = None, setpoint
     wt = _is_wt(vec)
     if setpoints is None:
         setpoints = (WT_INTEGRATOR_SETPOINTS if vec.obs_mode == "integrator" else WT_SETPOINTS) if wt else PH_SETPOINTS
-    if wt and vec.obs_mode == "stacking":
-        raise NotImplementedError("the staircase scenarios exist for the goal / integrator observation only")
+    # stacking observation: set_state / set_r do not touch the frame history (nonlinear_watertank.py:205-212 are inherited
+    # unchanged), so the first num_stack observations of a segment still show the frames of the reset -- reproduced
     steps = int(steps or (vec.cfg.max_step if wt else vec.cfg.max_episode_steps))
     K = np.asarray(K, dtype=np.float64).reshape(-1)
     S = vec.state_dim
@@ -98,7 +98,9 @@ def staircase(vec, policy: str, K, actor: Optional[V.ActorPack] = None, setpoint
     obs = torch.cat(obs_l)
     rewards = torch.cat(rew_l)
     res = {"obs": obs, "actions": torch.cat(act_l), "rewards": rewards, "totals": torch.cumsum(rewards.double(), 0)}
-    if wt:
+    if wt and vec.obs_mode == "stacking":   # env.state = the newest frame (update_state_P :1151-1153)
+        res.update(xs=obs[..., -3:-1], refs=obs[..., -1], integrators=None)
+    elif wt:
         res.update(xs=obs[..., :2], refs=obs[..., 2], integrators=obs[..., 3] if vec.obs_mode == "integrator" else None)
     else:
         res.update(ys=obs[..., 0], refs=obs[..., 1], integrators=obs[..., 2] if S == 3 else None)
@@ -109,14 +111,14 @@ ROBUST_TESTS = ((0.0024, 0.0019, 0.12), (0.0024, 0.0015, 0.12), (0.0024, 0.0015,
 
 
 def robust_sweep(K, actor: Optional[V.ActorPack] = None, params=ROBUST_TESTS, obs_mode="integrator", max_step=500,
-                 dtype=torch.float32, device="cuda", policy="agent", **cfg):
+                 dtype=torch.float32, device="cuda", policy="agent", setpoints=None, **cfg):
     """robust_test_nonlinear_watertank for any list / grid of (a1, a2, Kp): one env per parameter set, all sets in the
     same launches.  Returns (staircase result dict, params array [n, 3])."""
     p = np.asarray(params, dtype=np.float64).reshape(-1, 3)
     env = V.WaterTankVec(p.shape[0], dtype=dtype, device=device, obs_mode=obs_mode, max_step=max_step, **cfg)
     env.reset()
     env.reset_changable_parameters(torch.as_tensor(p[:, 0]), torch.as_tensor(p[:, 1]), torch.as_tensor(p[:, 2]))
-    res = staircase(env, policy, K, actor=actor, steps=max_step, resample_params=False)
+    res = staircase(env, policy, K, actor=actor, steps=max_step, resample_params=False, setpoints=setpoints)
     return res, p
 
 

@@ -378,6 +378,28 @@ class PHVec(_VecBase):
         self.tick += T
         return out
 
+    HOST_FIELDS = ("x", "y", "r", "I", "A", "B", "C", "qww_V", "qc_V", "t", "episode")
+
+    def rollout_host(self, host_state: dict, T: int, priorK, actor: Optional[ActorPack] = None, deterministic=False,
+                     ep_return_host: Optional[torch.Tensor] = None, **kw):
+        """Host-buffer entry (float flavour): host_state maps HOST_FIELDS to HOST tensors (x, A, B float64; y, r, I, C, qww_V,
+        qc_V float32; t, episode int32; pinned for full-speed copies).  Copies them in, runs the fused rollout, copies
+        ep_return and the final x, y, r, I back and synchronises -- every host<->device byte is inside this call."""
+        assert self.dtype == torch.float32
+        keep = []
+        a, out = _rollout_args(self, T, actor, priorK, deterministic, kw.pop("auto_reset", False), kw.pop("reward_scale", 1.0),
+                               kw.pop("gamma", 0.99), None, None, kw.pop("replay", None), False, kw.pop("stats", None), keep,
+                               kw.pop("a_std_log", None), keep_params=not kw.pop("resample_params", True))
+        assert not kw, f"unknown arguments {list(kw)}"
+        hs = L.PhState(**{k: L.ptr(host_state.get(k)) for k in self.HOST_FIELDS})
+        if ep_return_host is None:
+            ep_return_host = torch.empty(self.n, dtype=torch.float32, pin_memory=True)
+        L.check(L.lib().pime_ph_rollout_host_f32(C.byref(self.cfg), L.ptr(self.table), C.c_int64(self.n), C.byref(hs),
+                                                 C.byref(self._st), C.byref(a), L.ptr(ep_return_host), L.stream_ptr()))
+        self.tick += T
+        out["ep_return_host"] = ep_return_host
+        return out
+
     def get_changable_parameters(self):
         return self.qww_V, self.qc_V
 

@@ -357,3 +357,37 @@ def test_ph_auto_reset_and_stats(V):
     rew = host(out["buf_other"])[..., 0].astype(np.float64)
     np.testing.assert_allclose(st[4], rew.sum(), rtol=1e-5)
     assert int(env.episode.min()) == 4
+
+
+# ------------------------------------------------------------------------------------------------------ host-buffer entries
+def test_rollout_host_entries_equal_the_device_rollout(V):
+    """pime_wt_rollout_host_f32 / pime_ph_rollout_host_f32 (state in pinned host arrays, copies inside the call) produce
+    exactly what the device-resident rollout produces from the same state."""
+    n, seed = 1000, 9
+    sd = _torch_default_params("modular", 64, 4, 1, seed=2)
+    pack = V.ActorPack("modular", 4, 64, 1).update(sd)
+    a = V.WaterTankVec(n, dtype=torch.float32, seed=seed)
+    b = V.WaterTankVec(n, dtype=torch.float32, seed=seed)
+    a.reset(); b.reset()
+    hostst = {k: getattr(b, k).cpu().pin_memory() for k in ("h1", "h2", "r", "I", "a1", "a2", "Kp", "t", "episode")}
+    for k in ("h1", "h2", "r", "I"):
+        getattr(b, k).zero_()                      # the device copy must come from the host arrays
+    oa = a.rollout(200, -K_WT, actor=pack, replay=True)
+    ob = b.rollout_host(hostst, 200, -K_WT, actor=pack, replay=True)
+    assert torch.equal(oa["buf_state"], ob["buf_state"]) and torch.equal(oa["buf_other"], ob["buf_other"])
+    assert torch.equal(a.ep_return.cpu(), ob["ep_return_host"]) and torch.equal(a.h2.cpu(), hostst["h2"])
+
+    sdp = _torch_default_params("modular", 32, 3, 1, seed=3)
+    packp = V.ActorPack("modular", 3, 32, 1).update(sdp)
+    c = V.PHVec(n, dtype=torch.float32, seed=seed)
+    d = V.PHVec(n, dtype=torch.float32, seed=seed)
+    c.reset(); d.reset()
+    hp = {k: getattr(d, k).cpu().pin_memory() for k in d.HOST_FIELDS}
+    assert hp["x"].dtype == torch.float64 and hp["A"].dtype == torch.float64 and hp["y"].dtype == torch.float32
+    for k in ("x", "y", "A", "B"):
+        getattr(d, k).zero_()
+    oc = c.rollout(50, -K_PH, actor=packp, replay=True)
+    od = d.rollout_host(hp, 50, -K_PH, actor=packp, replay=True)
+    d.check_status()
+    assert torch.equal(oc["buf_state"], od["buf_state"]) and torch.equal(oc["buf_other"], od["buf_other"])
+    assert torch.equal(c.ep_return.cpu(), od["ep_return_host"]) and torch.equal(c.x.cpu(), hp["x"])
