@@ -196,11 +196,19 @@ enum {
     PIME_CRITIC_ADV = 2     /* CriticAdv                         S->H->H->H->1, ReLU   (net.py:274-277)          */
 };
 
+/* Arithmetic of the network forward (chosen per call; one packed image serves both):
+ *   PIME_PRECISION_TC    throughput: tcgen05 tensor cores, fp16 hidden operands, fp32 accumulation, tanh.approx
+ *                        (|a_avg - fp32 torch| <= 4e-3, measured 7e-4 .. 1.6e-3);
+ *   PIME_PRECISION_FP32  fidelity: every layer in fp32 on the CUDA cores, tanhf (|a_avg - fp32 torch| <= 2e-5): the
+ *                        reference's own arithmetic type, for parity runs and for the critic values of the learner. */
+enum { PIME_PRECISION_TC = 0, PIME_PRECISION_FP32 = 1 };
+
 typedef struct pime_actor_config {
     int32_t kind;           /* PIME_ACTOR_* / PIME_CRITIC_ADV                                   */
     int32_t state_dim;      /* S: 3, 4, 12, 30                                                  */
     int32_t mid_dim;        /* H: 32, 64, 128 or 256 (net_dim)                                  */
     int32_t integrator_dim; /* modular: 1                                                       */
+    int32_t precision;      /* PIME_PRECISION_*                                                 */
 } pime_actor_config;
 
 /* number of fp32 parameters expected in `params` (state_dict order) and size in bytes
@@ -219,7 +227,8 @@ int32_t pime_actor_block_list(const pime_actor_config *cfg, int32_t *out, int32_
  * integrator branch) followed by the fp16 weight blocks (<= 16 KB each) pre-tiled in the tcgen05 shared-memory operand
  * layout, so that one cp.async.bulk (TMA) copy brings a ready-to-use B operand.  First layers are stored as hi + lo
  * fp16 parts ([W_hi | W_hi | W_lo | b_hi b_lo] against [in_hi | in_lo | in_hi | 1 1]): fp32-grade products on the
- * tensor core; hidden-layer biases as [b_hi b_lo 0 ...] blocks against a constant ones operand. */
+ * tensor core; hidden-layer biases as [b_hi b_lo 0 ...] blocks against a constant ones operand.  The fp32 parameters
+ * themselves follow the fp16 blocks (the PIME_PRECISION_FP32 forward reads them). */
 int pime_actor_pack(const pime_actor_config *cfg, const float *params, void *pack, void *stream);
 
 /* a_avg[i] = net(obs[i,:])  (pre-tanh, pre-prior; get_action_noise net_residual.py:172-175 / :51-53).

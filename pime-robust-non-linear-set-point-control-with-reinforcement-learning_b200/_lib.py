@@ -16,6 +16,7 @@ REWARD = {"distance": 0, "square_distance": 1, "sparse": 2}
 WT_OBS_GOAL, WT_OBS_INTEGRATOR, WT_OBS_STACKING = 0, 1, 2
 PH_NO_INTEGRATOR, PH_INTEGRATOR, PH_INTEGRATOR_NOBOUND = 0, 1, 2
 ACTOR_PLAIN, ACTOR_MODULAR, CRITIC_ADV = 0, 1, 2
+PRECISION_TC, PRECISION_FP32 = 0, 1
 
 vp = C.c_void_p
 
@@ -53,7 +54,8 @@ class PhState(C.Structure):
 
 
 class ActorConfig(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("state_dim", C.c_int32), ("mid_dim", C.c_int32), ("integrator_dim", C.c_int32)]
+    _fields_ = [("kind", C.c_int32), ("state_dim", C.c_int32), ("mid_dim", C.c_int32), ("integrator_dim", C.c_int32),
+                ("precision", C.c_int32)]
 
 
 class RolloutArgs(C.Structure):

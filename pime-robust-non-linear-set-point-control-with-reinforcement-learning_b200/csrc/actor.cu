@@ -1,5 +1,5 @@
 // actor.cu -- weight packing and the stand-alone actor / critic forward on tcgen05 (see tc_mlp.cuh).
-#include "tc_mlp.cuh"
+#include "mlp_fp32.cuh"
 
 namespace pime {
 
@@ -8,6 +8,11 @@ namespace pime {
 __global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ tc::PackLayout L, const float *__restrict__ p,
                                                    uint8_t *__restrict__ out) {
     const int b = blockIdx.x;
+    if (b > L.nblk) {    // fp32 copy of the parameters behind the fp16 blocks (fidelity-mode forward)
+        float *dst = reinterpret_cast<float *>(out + L.f32_off);
+        for (int j = (b - L.nblk - 1) * blockDim.x + threadIdx.x; j < L.param_count; j += (gridDim.x - L.nblk - 1) * blockDim.x) dst[j] = p[j];
+        return;
+    }
     if (b == L.nblk) {   // fp32 output layer: weight vector + bias into the header
         float *ow = reinterpret_cast<float *>(out + tc::kOutWOff);
         for (int j = threadIdx.x; j < L.H; j += blockDim.x) ow[j] = p[L.out_w + j];
@@ -88,6 +93,33 @@ __global__ void __launch_bounds__(tc::kThreads, 1) actor_forward_kernel(tc::MlpP
     eng.teardown();
 }
 
+// Fidelity mode: fp32 CUDA-core forward (mlp_fp32.cuh), 32 rows per CTA.
+__global__ void __launch_bounds__(f32::kFThreads) actor_forward_fp32_kernel(const __grid_constant__ tc::PackLayout L,
+                                                                            const float *__restrict__ params, int64_t n,
+                                                                            const float *__restrict__ obs, float *__restrict__ out) {
+    extern __shared__ __align__(16) float sm32[];
+    float *tA = sm32, *tB = tA + f32::kTile, *sObs = tB + f32::kTile, *sOut = sObs + 32 * f32::kRS;
+    const int64_t r0 = (int64_t)blockIdx.x * f32::kFR;
+    for (int j = threadIdx.x; j < L.S * f32::kFR; j += blockDim.x) {
+        const int r = j / L.S, k = j % L.S;
+        const int64_t i = r0 + r < n ? r0 + r : n - 1;
+        sObs[k * f32::kRS + r] = obs[i * L.S + k];
+    }
+    __syncthreads();
+    f32::forward(L, params, sObs, tA, tB, sOut);
+    if (threadIdx.x < f32::kFR && r0 + threadIdx.x < n) out[r0 + threadIdx.x] = sOut[threadIdx.x];
+}
+
+static int launch_forward_fp32(const tc::PackLayout &L, const void *pack, int64_t n, const float *obs, float *out, cudaStream_t stream) {
+    PIME_CUDA(cudaFuncSetAttribute(actor_forward_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, f32::kSmemBytes));
+    const int64_t grid = (n + f32::kFR - 1) / f32::kFR;
+    PIME_REQUIRE(grid <= 0x7fffffffLL, "too many rows for one launch");
+    actor_forward_fp32_kernel<<<(unsigned)grid, f32::kFThreads, f32::kSmemBytes, stream>>>(
+        L, reinterpret_cast<const float *>((const uint8_t *)pack + L.f32_off), n, obs, out);
+    PIME_LAUNCH_CHECK();
+    return PIME_OK;
+}
+
 template <int KIND, int H>
 static int launch_forward_kh(const tc::PackLayout &L, const void *pack, int64_t n, const float *obs, float *out, cudaStream_t stream) {
     using G = tc::Geo<KIND, H>;
@@ -148,7 +180,7 @@ int pime_actor_pack(const pime_actor_config *cfg, const float *params, void *pac
     PIME_REQUIRE(tc::make_pack_layout(*cfg, L), "unsupported actor dimensions (H in {32,64,128,256}, S <= 32, modular: S-1 <= 3)");
     PIME_REQUIRE(((uintptr_t)pack & 127) == 0, "pack must be 128-byte aligned");
     if (int rc = require_device()) return rc;
-    pack_kernel<<<L.nblk + 1, 256, 0, (cudaStream_t)stream>>>(L, params, (uint8_t *)pack);
+    pack_kernel<<<L.nblk + 1 + 16, 256, 0, (cudaStream_t)stream>>>(L, params, (uint8_t *)pack);
     PIME_LAUNCH_CHECK();
     return PIME_OK;
 }
@@ -159,6 +191,8 @@ int pime_actor_forward(const pime_actor_config *cfg, const void *pack, int64_t n
     PIME_REQUIRE(tc::make_pack_layout(*cfg, L), "unsupported actor dimensions");
     if (int rc = require_device()) return rc;
     if (n <= 0) return PIME_OK;
+    if (cfg->precision == PIME_PRECISION_FP32) return launch_forward_fp32(L, pack, n, obs, a_avg, (cudaStream_t)stream);
+    PIME_REQUIRE(cfg->precision == PIME_PRECISION_TC, "precision");
     switch (cfg->kind) {
         case PIME_ACTOR_PLAIN: return launch_forward_k<PIME_ACTOR_PLAIN>(L, pack, n, obs, a_avg, (cudaStream_t)stream);
         case PIME_ACTOR_MODULAR: return launch_forward_k<PIME_ACTOR_MODULAR>(L, pack, n, obs, a_avg, (cudaStream_t)stream);

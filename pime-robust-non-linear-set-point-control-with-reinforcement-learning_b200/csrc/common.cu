@@ -43,6 +43,17 @@ int require_device() {
     return cached;
 }
 
+int device_sm_count() {
+    static thread_local int cached[64] = {0};
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
+    if (cached[dev] == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kNumSMs;
+        cached[dev] = v;
+    }
+    return cached[dev];
+}
+
 }  // namespace pime
 
 extern "C" {

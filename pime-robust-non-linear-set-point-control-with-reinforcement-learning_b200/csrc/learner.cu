@@ -557,10 +557,13 @@ __device__ __forceinline__ AdamCoef adam_coef(const StepParams &p) {
     c.one_m_b1 = 1.0f - p.beta1; c.b2 = p.beta2; c.one_m_b2 = 1.0f - p.beta2; c.eps = p.eps;
     return c;
 }
+// every operation is spelled out (no compiler-chosen FMA contraction): the fused weight-gradient epilogue and the
+// stand-alone Adam kernel of the data-parallel path must produce bit-identical parameters and moments
 __device__ __forceinline__ float adam_update(const AdamCoef &c, float g, float theta, float &m, float &v) {
-    m = m + (g - m) * c.one_m_b1;
-    v = c.b2 * v + c.one_m_b2 * g * g;
-    return theta - c.lr_bc1 * m / (sqrtf(v) * c.inv_sqrt_bc2 + c.eps);
+    m = __fmaf_rn(c.one_m_b1, __fsub_rn(g, m), m);                              // lerp(exp_avg, grad, 1 - beta1)
+    v = __fmaf_rn(__fmul_rn(c.one_m_b2, g), g, __fmul_rn(c.b2, v));             // beta2 v + (1 - beta2) g g
+    const float den = __fmaf_rn(sqrtf(v), c.inv_sqrt_bc2, c.eps);
+    return __fsub_rn(theta, __fdiv_rn(__fmul_rn(c.lr_bc1, m), den));
 }
 
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, bool valid) {

@@ -15,6 +15,7 @@ namespace pime {
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 int require_device();  // PIME_OK or PIME_ENODEV (message set)
+int device_sm_count();  // multiprocessors of the current device (148 on B200); kNumSMs when the query fails
 
 #define PIME_CUDA(call)                                                        \
     do {                                                                       \

@@ -4,6 +4,7 @@
 #pragma once
 
 #include "plants.cuh"
+#include "mlp_fp32.cuh"
 #include "tc_mlp.cuh"
 
 namespace pime {
@@ -290,15 +291,21 @@ template <typename Plant> struct Stepper {
 };
 
 // ------------------------------------------------------------------------------------------------ the kernels
-// Fused rollout with an actor: 256 envs per CTA (two groups of 128), see tc_mlp.cuh for the roles.
+// Fused rollout with an actor: 256 envs per tile (two groups of 128), see tc_mlp.cuh for the roles.  PERSISTENT: one CTA
+// per SM walks over the tiles blockIdx.x, blockIdx.x + gridDim.x, ... as ONE continuous sequence of network passes -- TMEM
+// allocation, barrier initialisation, the fp32 layer tables, the fill / drain of the software pipeline and the statistics
+// tail are paid once per SM instead of once per tile (the pH sweep of BASELINE configs[3] is 32 768 tiles of only 50 steps).
+// At a tile boundary the owner stores its env, loads the env of the next tile and writes that observation as the next pass's
+// input, so the workers / MMA / TMA roles never notice the boundary.
 template <typename Plant, int KIND, int H>
-__global__ void __launch_bounds__(tc::kThreads, 1) rollout_kernel(Plant plant, tc::MlpParams mp, RolloutParams rp) {
+__global__ void __launch_bounds__(tc::kThreads, 1) rollout_kernel(Plant plant, tc::MlpParams mp, RolloutParams rp, int n_tiles) {
     extern __shared__ __align__(1024) uint8_t smem[];
     tc::Engine<KIND, H> eng;
     eng.setup(smem, mp);
     double (*red)[4] = eng.red();
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int passes = 2 * rp.T;
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int passes = 2 * rp.T * my_tiles;
     bool fault = false;
 
     if (warp < 8) {
@@ -306,14 +313,14 @@ __global__ void __launch_bounds__(tc::kThreads, 1) rollout_kernel(Plant plant, t
     } else if (warp < 12) {
         const int row = tid - tc::kWorkerThreads;
         const int64_t n = rp.n;
-        const int64_t i0 = (int64_t)blockIdx.x * tc::kTileEnvs + row, i1 = i0 + tc::kRows;
-        const bool live0 = i0 < n, live1 = i1 < n;
-        const int64_t ii0 = live0 ? i0 : n - 1, ii1 = live1 ? i1 : n - 1;  // tail rows shadow the last env and write nothing
-        typename Plant::Env env0, env1;
-        plant.load(env0, ii0, n);
-        plant.load(env1, ii1, n);
         Stepper<Plant> sp;
         float obs[kMaxS];
+        typename Plant::Env env0, env1;
+        int64_t i0 = (int64_t)blockIdx.x * tc::kTileEnvs + row, i1 = i0 + tc::kRows;
+        bool live0 = i0 < n, live1 = i1 < n;
+        int64_t ii0 = live0 ? i0 : n - 1, ii1 = live1 ? i1 : n - 1;  // tail rows shadow the last env and write nothing
+        plant.load(env0, ii0, n);
+        plant.load(env1, ii1, n);
         plant.observe(env0, obs);
         eng.write_obs(row, 0, obs);
         plant.observe(env1, obs);
@@ -324,23 +331,38 @@ __global__ void __launch_bounds__(tc::kThreads, 1) rollout_kernel(Plant plant, t
 #else
 #define PIME_TICK(acc)
 #endif
-        for (int s = 0; s < rp.T; ++s) {
-            const bool more = s + 1 < rp.T;
-            {   // group 0: its network pass is 2s; the workers run group 1's pass while this thread steps the plant
-                const float a_avg = eng.read_out(row, 2 * s);
-                PIME_TICK(c_wait)
-                plant.observe(env0, obs);
-                sp.step(plant, rp, env0, obs, a_avg, s, ii0, live0);
-                if (more) { plant.observe(env0, obs); eng.write_obs(row, 0, obs); }
-                PIME_TICK(c_work)
-            }
-            {
-                const float a_avg = eng.read_out(row, 2 * s + 1);
-                PIME_TICK(c_wait)
-                plant.observe(env1, obs);
-                sp.step(plant, rp, env1, obs, a_avg, s, ii1, live1);
-                if (more) { plant.observe(env1, obs); eng.write_obs(row, 1, obs); }
-                PIME_TICK(c_work)
+        int q = 0;   // running pass index of this CTA (group g of step s of tile k: q = 2 (k T + s) + g)
+        for (int k = 0; k < my_tiles; ++k) {
+            const bool next_tile = k + 1 < my_tiles;
+            const int64_t j0 = i0 + (int64_t)gridDim.x * tc::kTileEnvs, j1 = j0 + tc::kRows;   // this row's envs in the next tile
+            for (int s = 0; s < rp.T; ++s) {
+                const bool more = s + 1 < rp.T;
+                {   // group 0: the workers run group 1's pass while this thread steps the plant
+                    const float a_avg = eng.read_out(row, q++);
+                    PIME_TICK(c_wait)
+                    plant.observe(env0, obs);
+                    sp.step(plant, rp, env0, obs, a_avg, s, ii0, live0);
+                    if (!more && next_tile) {
+                        if (live0) plant.store(env0, i0, n);
+                        i0 = j0; live0 = i0 < n; ii0 = live0 ? i0 : n - 1;
+                        plant.load(env0, ii0, n);
+                    }
+                    if (more || next_tile) { plant.observe(env0, obs); eng.write_obs(row, 0, obs); }
+                    PIME_TICK(c_work)
+                }
+                {
+                    const float a_avg = eng.read_out(row, q++);
+                    PIME_TICK(c_wait)
+                    plant.observe(env1, obs);
+                    sp.step(plant, rp, env1, obs, a_avg, s, ii1, live1);
+                    if (!more && next_tile) {
+                        if (live1) plant.store(env1, i1, n);
+                        i1 = j1; live1 = i1 < n; ii1 = live1 ? i1 : n - 1;
+                        plant.load(env1, ii1, n);
+                    }
+                    if (more || next_tile) { plant.observe(env1, obs); eng.write_obs(row, 1, obs); }
+                    PIME_TICK(c_work)
+                }
             }
         }
 #ifdef PIME_PROFILE_OWNER
@@ -359,6 +381,54 @@ __global__ void __launch_bounds__(tc::kThreads, 1) rollout_kernel(Plant plant, t
     eng.teardown();  // __syncthreads inside: red[][] is complete
     if (rp.stats && tid < 6) atomicAdd(rp.stats + tid, red[tid][0] + red[tid][1] + red[tid][2] + red[tid][3]);
     if (fault && rp.status) atomicMin(rp.status, (int32_t)PIME_ERANGE);
+}
+
+// Fidelity mode of the fused rollout (actor.precision = PIME_PRECISION_FP32): the same Stepper, the network in fp32 on the
+// CUDA cores (mlp_fp32.cuh).  32 envs per CTA: threads 0..31 own one env each, all 256 threads evaluate the layers.
+template <typename Plant>
+__global__ void __launch_bounds__(f32::kFThreads) rollout_fp32_kernel(Plant plant, const __grid_constant__ tc::PackLayout L,
+                                                                      const float *__restrict__ params, RolloutParams rp) {
+    extern __shared__ __align__(16) float sm32[];
+    __shared__ double red[6][4];
+    float *tA = sm32, *tB = tA + f32::kTile, *sObs = tB + f32::kTile, *sOut = sObs + 32 * f32::kRS;
+    const int tid = threadIdx.x;
+    const bool owner = tid < f32::kFR;
+    const int64_t n = rp.n;
+    const int64_t i = (int64_t)blockIdx.x * f32::kFR + (owner ? tid : 0);
+    const bool live = owner && i < n;
+    const int64_t ii = i < n ? i : n - 1;
+    typename Plant::Env env;
+    if (owner) plant.load(env, ii, n);
+    Stepper<Plant> sp;
+    float obs[kMaxS];
+    if (tid < 24) red[tid / 4][tid % 4] = 0.0;
+    for (int s = 0; s < rp.T; ++s) {
+        if (owner) {
+            plant.observe(env, obs);
+#pragma unroll
+            for (int k = 0; k < Plant::kObsMax; ++k)
+                if (k < rp.S) sObs[k * f32::kRS + tid] = obs[k];
+        }
+        __syncthreads();
+        f32::forward(L, params, sObs, tA, tB, sOut);
+        if (owner) sp.step(plant, rp, env, obs, sOut[tid], s, ii, live);
+    }
+    if (live) plant.store(env, i, n);
+    if (rp.stats && owner) sp.reduce_warp(red, 0);
+    __syncthreads();
+    if (rp.stats && tid < 6) atomicAdd(rp.stats + tid, red[tid][0]);
+    if (owner && sp.fault && rp.status) atomicMin(rp.status, (int32_t)PIME_ERANGE);
+}
+
+template <typename Plant>
+int launch_rollout_fp32(const Plant &plant, const tc::PackLayout &L, const void *pack, const RolloutParams &rp, cudaStream_t stream) {
+    auto kern = rollout_fp32_kernel<Plant>;
+    PIME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, f32::kSmemBytes));
+    const int64_t grid = (rp.n + f32::kFR - 1) / f32::kFR;
+    PIME_REQUIRE(grid <= 0x7fffffffLL, "too many envs for one launch");
+    kern<<<(unsigned)grid, f32::kFThreads, f32::kSmemBytes, stream>>>(plant, L, reinterpret_cast<const float *>((const uint8_t *)pack + L.f32_off), rp);
+    PIME_LAUNCH_CHECK();
+    return PIME_OK;
 }
 
 // Prior-only policy (no actor): one thread per env, nothing but the plant and the prior.
@@ -400,9 +470,12 @@ int launch_rollout_kh(const Plant &plant, const tc::PackLayout *L, const void *p
     auto kern = rollout_kernel<Plant, KIND, H>;
     PIME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SmemBytes));
     const tc::MlpParams mp = tc::make_mlp_params(*L, pack);
-    const int64_t grid = (rp.n + tc::kTileEnvs - 1) / tc::kTileEnvs;
-    PIME_REQUIRE(grid <= 0x7fffffffLL, "too many envs for one launch");
-    kern<<<(unsigned)grid, tc::kThreads, G::SmemBytes, stream>>>(plant, mp, rp);
+    const int64_t tiles = (rp.n + tc::kTileEnvs - 1) / tc::kTileEnvs;
+    const int sms = device_sm_count();
+    const int64_t grid = tiles < sms ? tiles : sms;   // one persistent CTA per SM (227 KB of shared memory each)
+    PIME_REQUIRE(tiles <= 0x7fffffffLL && 2 * (int64_t)rp.T * ((tiles + grid - 1) / grid) <= 0x7fffffffLL,
+                 "too many env steps for one launch");
+    kern<<<(unsigned)grid, tc::kThreads, G::SmemBytes, stream>>>(plant, mp, rp, (int)tiles);
     PIME_LAUNCH_CHECK();
     return PIME_OK;
 }
@@ -450,6 +523,7 @@ inline int fill_rollout_params(const pime_rollout_args *a, int64_t n, int S, Rol
         PIME_REQUIRE(a->actor->kind == PIME_ACTOR_PLAIN || a->actor->kind == PIME_ACTOR_MODULAR, "actor kind");
         PIME_REQUIRE(a->actor->state_dim == S, "actor state_dim does not match the env observation");
         PIME_REQUIRE(tc::make_pack_layout(*a->actor, L), "unsupported actor dimensions");
+        PIME_REQUIRE(a->actor->precision == PIME_PRECISION_TC || a->actor->precision == PIME_PRECISION_FP32, "actor precision");
     }
     return PIME_OK;
 }

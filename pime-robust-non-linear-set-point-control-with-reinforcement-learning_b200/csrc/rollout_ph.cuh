@@ -28,8 +28,10 @@ int ph_rollout_impl(const pime_ph_config *cfg, const T *table, int64_t n, const 
     g.ep_return = (T *)st->ep_return; g.last_x = (double *)st->last_x; g.t = st->t; g.episode = st->episode;
     cudaStream_t s = (cudaStream_t)stream;
     if (!rp.has_actor) return launch_rollout_prior<PhGlue<T>>(g, rp, s);
+    PIME_REQUIRE(args->actor->kind != PIME_ACTOR_MODULAR || cfg->integrator_mode != PIME_PH_NO_INTEGRATOR,
+                 "the modular actor needs the integrator observation");
+    if (args->actor->precision == PIME_PRECISION_FP32) return launch_rollout_fp32<PhGlue<T>>(g, L, args->actor_pack, rp, s);
     if (args->actor->kind == PIME_ACTOR_MODULAR) {
-        PIME_REQUIRE(cfg->integrator_mode != PIME_PH_NO_INTEGRATOR, "the modular actor needs the integrator observation");
         return launch_rollout_k<PhGlue<T>, PIME_ACTOR_MODULAR>(g, &L, args->actor_pack, rp, L.H, s);
     }
     return launch_rollout_k<PhGlue<T>, PIME_ACTOR_PLAIN>(g, &L, args->actor_pack, rp, L.H, s);

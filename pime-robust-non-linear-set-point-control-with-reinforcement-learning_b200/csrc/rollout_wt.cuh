@@ -33,13 +33,16 @@ int wt_rollout_impl(const pime_wt_config *cfg, int64_t n, const pime_wt_state *s
         fill(g);
         if (!rp.has_actor) return launch_rollout_prior<WtGlue<T, true>>(g, rp, s);
         PIME_REQUIRE(args->actor->kind == PIME_ACTOR_PLAIN, "the stacking observation goes with the plain actor");
+        if (args->actor->precision == PIME_PRECISION_FP32) return launch_rollout_fp32<WtGlue<T, true>>(g, L, args->actor_pack, rp, s);
         return launch_rollout_k<WtGlue<T, true>, PIME_ACTOR_PLAIN>(g, &L, args->actor_pack, rp, L.H, s);
     }
     WtGlue<T, false> g;
     fill(g);
     if (!rp.has_actor) return launch_rollout_prior<WtGlue<T, false>>(g, rp, s);
+    PIME_REQUIRE(args->actor->kind != PIME_ACTOR_MODULAR || cfg->obs_mode == PIME_WT_OBS_INTEGRATOR,
+                 "the modular actor needs the integrator observation");
+    if (args->actor->precision == PIME_PRECISION_FP32) return launch_rollout_fp32<WtGlue<T, false>>(g, L, args->actor_pack, rp, s);
     if (args->actor->kind == PIME_ACTOR_MODULAR) {
-        PIME_REQUIRE(cfg->obs_mode == PIME_WT_OBS_INTEGRATOR, "the modular actor needs the integrator observation");
         return launch_rollout_k<WtGlue<T, false>, PIME_ACTOR_MODULAR>(g, &L, args->actor_pack, rp, L.H, s);
     }
     return launch_rollout_k<WtGlue<T, false>, PIME_ACTOR_PLAIN>(g, &L, args->actor_pack, rp, L.H, s);

@@ -102,6 +102,7 @@ struct PackLayout {
     int nin, nterms, KP;   // first-layer operand: inputs, split terms (3 or 2), K padded to a multiple of 16
     int nblk;
     int f16_bytes, total_bytes;
+    int f32_off;           // byte offset of the fp32 copy of the parameters (state_dict order) behind the fp16 blocks
     int src[12];           // offsets of the state_dict tensors inside `params`
     int out_w, out_b;      // offsets of the last layer's weight vector / bias inside `params`
     int l1i_w, l1i_b;      // modular: offsets of integrator_net.0's weight / bias inside `params`
@@ -205,7 +206,8 @@ inline bool make_pack_layout(const pime_actor_config &c, PackLayout &L) {
         L.out_w = L.src[6]; L.out_b = L.src[7];                            // net.6: fp32 dot product inside the last epilogue
     }
     if (!ok) return false;
-    L.total_bytes = kHeaderBytes + L.f16_bytes;
+    L.f32_off = (kHeaderBytes + L.f16_bytes + 15) & ~15;
+    L.total_bytes = (L.f32_off + 4 * L.param_count + 15) & ~15;
     return true;
 }
 

@@ -407,6 +407,7 @@ class AgentPPO:
         self.fused_max_batch = 4096     # beyond it the cuBLAS autograd step is faster than the fp32 SIMT kernels
         self._fused = None
         self.learner_path = None        # which minibatch step the last update_net ran (reported by bench.py)
+        self.value_fp32_max_rows = 1 << 20
 
     # ---- construction
     def _make_actor(self, net_dim, state_dim, action_dim, **kw):
@@ -511,8 +512,12 @@ class AgentPPO:
 
     # ---- learning
     def _values(self, buf_state):
-        """Critic over the whole buffer: the tcgen05 forward kernel (the reference loops 1024-row torch slices, agent.py:619)."""
-        return self._pack("cri").forward(buf_state)
+        """Critic over the whole buffer in one launch (the reference loops 1024-row torch slices, agent.py:619).  Buffers up to
+        ``value_fp32_max_rows`` rows use the fidelity mode (fp32 CUDA cores: the reference's arithmetic, so GAE sees the
+        values torch would produce); larger ones the tcgen05 engine (fp16 hidden operands, ~1e-3 of the output scale)."""
+        pack = self._pack("cri")
+        pack.set_precision("fp32" if buf_state.shape[0] <= self.value_fp32_max_rows else "tc")
+        return pack.forward(buf_state)
 
     def _time_major(self, buffer, x):
         n = buffer.num_envs

@@ -34,6 +34,7 @@ class ActorPack:
 
     ``kind``: 'plain' (ActorResidualPPO, net_residual.py:6-66), 'modular' (ActorResidualIntegratorModularPPO,
     :138-205) or 'critic' (CriticAdv, net.py:274-277).  ``update(state_dict)`` re-packs after a learner step.
+    ``precision``: 'tc' (default) = throughput mode, |a_avg - fp32 torch| <= 4e-3; 'fp32' = fidelity mode, <= 2e-5.
     """
 
     KEYS = {
@@ -46,11 +47,13 @@ class ActorPack:
     KEYS["critic"] = KEYS["plain"]
     KIND = {"plain": L.ACTOR_PLAIN, "modular": L.ACTOR_MODULAR, "critic": L.CRITIC_ADV}
 
-    def __init__(self, kind: str, state_dim: int, mid_dim: int, integrator_dim: int = 0, device="cuda"):
+    PRECISION = {"tc": L.PRECISION_TC, "fp32": L.PRECISION_FP32}
+
+    def __init__(self, kind: str, state_dim: int, mid_dim: int, integrator_dim: int = 0, device="cuda", precision="tc"):
         self.kind = kind
         self.device = _require_cuda(device)
         self.cfg = L.ActorConfig(kind=self.KIND[kind], state_dim=state_dim, mid_dim=mid_dim,
-                                 integrator_dim=integrator_dim if kind == "modular" else 0)
+                                 integrator_dim=integrator_dim if kind == "modular" else 0, precision=self.PRECISION[precision])
         self.param_count = int(L.lib().pime_actor_param_count(C.byref(self.cfg)))
         nbytes = int(L.lib().pime_actor_pack_bytes(C.byref(self.cfg)))
         if self.param_count < 0 or nbytes < 0:
@@ -73,6 +76,12 @@ class ActorPack:
             v = state_dict["a_std_log"]
             self.a_std_log = float(v.reshape(-1)[0]) if hasattr(v, "reshape") else float(v)
         return self.update_from_flat()
+
+    def set_precision(self, precision: str) -> "ActorPack":
+        """'tc': tcgen05 throughput engine (fp16 hidden operands); 'fp32': fidelity mode (fp32 CUDA cores, tanhf).  The packed
+        image holds both forms, so switching needs no re-pack."""
+        self.cfg.precision = self.PRECISION[precision]
+        return self
 
     def update_from_flat(self) -> "ActorPack":
         """Re-pack from ``self.flat`` (fp32 parameters in state_dict order, already on the device)."""

@@ -112,3 +112,28 @@ def test_repack_after_update_changes_output(V):
     sd["net.6.bias"] = sd["net.6.bias"] + 1.0
     b = pack.update(sd).forward(obs)
     np.testing.assert_allclose(host(b - a), 1.0, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind,H,S,D", [("modular", 256, 4, 1), ("modular", 128, 3, 1), ("plain", 256, 30, 0), ("critic", 256, 4, 0),
+                                        ("plain", 32, 3, 0)])
+@pytest.mark.parametrize("n", [1, 33, 40000])
+def test_fidelity_mode_forward_vs_torch_fp32(V, kind, H, S, D, n):
+    """PIME_PRECISION_FP32 (fp32 CUDA cores, tanhf): |a_avg - fp32 torch| <= 2e-5 at every size, ragged row counts included."""
+    sd = _torch_default_params(kind, H, S, D, seed=H + S)
+    obs = torch.as_tensor(np.random.default_rng(n).uniform(-1, 10, (n, S)).astype(np.float32)).cuda()
+    if S == 4:
+        obs[:, 3] = torch.as_tensor(np.random.default_rng(1).uniform(-25, 25, n).astype(np.float32)).cuda()
+    pack = V.ActorPack(kind, S, H, D, precision="fp32").update(sd)
+    got = host(pack.forward(obs))
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        want = host(_torch_forward(kind, sd, obs, relu=kind == "critic"))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    err = np.abs(got - want.reshape(-1)).max()
+    print(f"fidelity {kind}-{H} S={S} n={n}: max |a_avg err| = {err:.2e}")
+    assert err <= 2e-5
+    # the same packed image still serves the throughput engine
+    tc = host(pack.set_precision("tc").forward(obs))
+    np.testing.assert_allclose(tc, want.reshape(-1), atol=ATOL, rtol=RTOL)

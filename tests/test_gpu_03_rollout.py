@@ -216,6 +216,37 @@ def test_wt_full_size_actor_per_step_parity_and_trajectory_tolerance(V, oracle):
         assert np.median(dret) <= 2e-3 and dret.max() <= 6e-2
 
 
+def test_wt_full_size_closed_loop_fidelity_mode_max_norm(V, oracle):
+    """The same scenario (Modular-256, random high-gain last layer, 200 closed-loop steps, fp64 plant) with the actor in
+    FIDELITY mode (fp32 CUDA cores, tanhf): the whole fused step now meets MAX-NORM bounds against the oracle's
+    fp64-plant / fp32-actor trajectory -- per step |a_raw - oracle net| <= 2e-5, and over the whole episode (every env, every
+    step) levels <= 2e-3, integrated error <= 2e-2, episode return <= 1e-4 relative.  (The throughput mode needs quantiles,
+    see the test above: its fp16 hidden operands are amplified by this untrained policy's loop gain.)"""
+    n, T = 256, 200
+    rng = np.random.default_rng(11)
+    d = random_wt_inputs(rng, n); d["t"][:] = 0
+    d["h1"] = rng.uniform(0, 10, n); d["h2"] = rng.uniform(0, 10, n); d["I"][:] = 0
+    sd = _torch_default_params("modular", 256, 4, 1, seed=5)
+    pack = V.ActorPack("modular", 4, 256, 1, precision="fp32").update(sd)
+    acfg = oracle.ActorCfg(kind=1, state_dim=4, mid_dim=256, integrator_dim=1)
+    params = oracle.pack_actor_params(sd, 1)
+    eps = rng.normal(0, 1, (T, n)).astype(np.float32)
+    o = _wt_oracle_rollout(oracle, d, T, acfg=acfg, params=params, eps=eps)
+    a_std = np.float32(np.exp(np.float32(-0.5)))
+    env = V.WaterTankVec(n, dtype=torch.float64, reward_type="distance", noise_scale=0.0)
+    load_wt(env, d)
+    out = env.rollout(T, -K_WT, actor=pack, eps=dev(eps), replay=True, want_actions=True)
+    bs, bo = host(out["buf_state"]), host(out["buf_other"])
+    a_net = oracle.actor_forward(acfg, params, bs.reshape(-1, 4)).reshape(T, n)
+    err1 = np.abs(bo[..., 2] - (a_net + eps * a_std)).max()
+    dh = np.abs(bs[..., :2] - o["buf_state"][..., :2]).max()
+    dI = np.abs(bs[..., 3] - o["buf_state"][..., 3]).max()
+    dret = (np.abs(host(env.ep_return) - o["ep_return"]) / np.abs(o["ep_return"])).max()
+    print(f"fidelity mode: a_raw per-step err {err1:.2e}; trajectory max-norm: levels {dh:.2e}, I {dI:.2e}, return rel {dret:.2e}")
+    assert err1 <= 2e-5
+    assert dh <= 2e-3 and dI <= 2e-2 and dret <= 1e-4
+
+
 def test_wt_in_kernel_rng_reproducible_and_shard_invariant(V):
     """Philox keyed by (seed, global env id, tick): identical bits for any split of the env range (DESIGN.md multi-GPU)."""
     n, T = 4096, 20
@@ -311,19 +342,22 @@ def test_ph_reference_closed_loop_fixture(V, golden):
             assert bool(done[0]) == bool(rows[s, 5])
 
 
-def test_ph_explore_env_fixture(V, golden):
-    """pH explore_env fixture: y(x) is a staircase, so a 1-ulp action difference can move an episode to a neighbouring
-    table entry; stated tolerance: first 3 steps of every episode within 5e-3, >= 80% of the episodes within 5e-2
-    over all 50 steps (the steep part of the titration curve amplifies actor rounding)."""
+@pytest.mark.parametrize("precision,dtype", [("fp32", torch.float64), ("fp32", torch.float32), ("tc", torch.float64)])
+def test_ph_explore_env_fixture(V, golden, precision, dtype):
+    """pH explore_env fixture (the reference's own rollout, agent_residual.py:52-69).  y(x) is a staircase: an action that
+    differs in the last bits can move a step to the neighbouring table entry (<= 0.014 pH on the steep part of the curve),
+    which the PI loop then pulls back.  Stated tolerance, for EVERY episode and every step: 5e-2 on the observations
+    (y, r, I), first 3 steps 5e-3 -- in fidelity mode with the fp64 and the fp32 plant (whose x, A, B and table index are
+    fp64) and in throughput mode (fp16 hidden operands)."""
     g = golden("explore")
     sd = _fixture_sd(g, "ph")
     H = int(g["ph.H"])
-    pack = V.ActorPack("modular", 3, H, 1).update(sd)
+    pack = V.ActorPack("modular", 3, H, 1, precision=precision).update(sd)
     T = 50
     bs, bo, resets = g["ph.explore.buf_state"], g["ph.explore.buf_other"], g["ph.explore.resets"]
     n_ep = bs.shape[0] // T
     resets = resets[:n_ep]
-    env = V.PHVec(n_ep, dtype=torch.float64)
+    env = V.PHVec(n_ep, dtype=dtype)
     env.reset()
     table = host(V.ph_table(env.cfg, env.device)[0])
     d = dict(qww_V=resets[:, 0], qc_V=resets[:, 1], x=resets[:, 2], r=resets[:, 3], A=resets[:, 4], B=resets[:, 5], C=resets[:, 6],
@@ -337,8 +371,8 @@ def test_ph_explore_env_fixture(V, golden):
     want = bs[:n_ep * T].reshape(n_ep, T, 3)
     np.testing.assert_allclose(got[:, :3], want[:, :3], atol=5e-3, rtol=0)
     ok = np.array([np.allclose(got[e], want[e], atol=5e-2, rtol=0) for e in range(n_ep)])
-    print("pH explore episodes within tolerance:", ok.sum(), "/", n_ep)
-    assert ok.mean() >= 0.8
+    print(f"pH explore [{precision}, {dtype}] episodes within tolerance:", ok.sum(), "/", n_ep, "max err", np.abs(got - want).max())
+    assert ok.all()
     assert np.array_equal(host(out["buf_other"]).transpose(1, 0, 2).reshape(-1, 4)[:, 1], bo[:n_ep * T, 1])
 
 

