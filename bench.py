@@ -478,7 +478,7 @@ def extra_config4(V, world, rank, dist, barrier, pk, steps=5, warmup=2):
     return out
 
 
-def extra_config5(world, rank, dist, barrier, n=1 << 13, batch=4096, repeat=2, iters=2):
+def extra_config5(world, rank, dist, barrier, n=1 << 16, batch=1 << 17, repeat=2, iters=2):
     """BASELINE configs[4]: full residual PPO training -- explore (one fused launch into the GPU-resident replay), critic
     values + GAE kernels, repeat * T * n / batch minibatch steps with the gradient all-reduce when world > 1."""
     import torch

@@ -346,6 +346,23 @@ int pime_ppo_step(const pime_ppo_args *args, void *stream);
  * the ones that call left in `state`. */
 int pime_ppo_apply_grad(const pime_ppo_args *args, const float *grad, float scale, void *stream);
 
+/* Large minibatches (BASELINE configs[4]: 131 072 rows) on the tcgen05 tensor cores (csrc/learner_tc.cu): the batch is cut
+ * into 128-row tiles, every layer of the forward pass, of the data-gradient chain and every weight gradient is a GEMM whose
+ * operands are fp16 hi + lo pairs (three MMAs per product: fp32-grade sums) streamed by TMA, accumulated in TMEM.
+ *   pime_ppo_grad_tc     gradient of obj_united over the rows args->idx into grad[pime_ppo_theta_count] (theta's layout;
+ *                        zeroed first), the loss-ring row and the Adam bias corrections of the step; theta is NOT touched.
+ *                        work_tc: pime_ppo_tc_work_bytes(actor, batch) bytes of device scratch, 256-byte aligned.
+ *                        mid_dim 128 or 256, plain or modular actor, 2 <= batch <= 2^20.  args->theta_t / adam_* / work unused.
+ *   pime_ppo_apply_grad  (above) applies Adam; all-reduce grad in between when the job is data parallel.
+ *   pime_ppo_close_step  increments the step count and clears the next loss-ring row (the small-batch pime_ppo_step does
+ *                        this itself); call it last.
+ *   pime_ppo_tc_layout   byte offset / unit count of the intermediate matrices inside work_tc (X, activations, pre-activation
+ *                        gradients; 17 pairs) -- lets the tests compare every stage with torch. */
+int64_t pime_ppo_tc_work_bytes(const pime_actor_config *actor, int32_t batch);
+int pime_ppo_tc_layout(const pime_actor_config *actor, int32_t batch, int64_t *out34);
+int pime_ppo_grad_tc(const pime_ppo_args *args, void *work_tc, float *grad, void *stream);
+int pime_ppo_close_step(const pime_ppo_args *args, void *stream);
+
 /* misc */
 int pime_abi_version(void);
 const char *pime_last_error(void);

@@ -222,16 +222,25 @@ class FusedLearner:
         self.loss_ring = torch.zeros((self.RING, 4), dtype=torch.float32, device=device)
         self.work = None
         self.grad = None        # distributed: flat gradient of this rank's minibatch, all-reduced before the Adam kernel
+        self.work_tc = None     # scratch of the tensor-core step (activations / gradients of one minibatch in T-format)
         self.steps = 0          # host mirror of the device step count
         self._args = None
         self._step_fn = V.L.lib().pime_ppo_step
         self._keys = (V.ActorPack.KEYS[act.kind], V.ActorPack.KEYS["critic"])
 
     @staticmethod
+    def use_tc(agent, batch_size):
+        """Batches from ``tc_learner_min_batch`` rows on take the tcgen05 step (pime_ppo_grad_tc: 128-row tiles, hi / lo fp16
+        GEMMs); it needs net_dim 128 or 256."""
+        return batch_size >= agent.tc_learner_min_batch and agent.net_dim in (128, 256) and batch_size <= (1 << 20)
+
+    @staticmethod
     def eligible(agent, batch_size):
         """Everything trainable (the frozen_* variants keep the autograd step), one action.  Under torch.distributed the
-        step becomes rows + weight-gradient kernels -> flat all-reduce -> Adam kernel (pime_ppo_apply_grad)."""
-        if agent.act.kind not in ("plain", "modular") or not 2 <= batch_size <= agent.fused_max_batch:
+        step becomes gradient kernels -> flat all-reduce -> Adam kernel (pime_ppo_apply_grad)."""
+        if agent.act.kind not in ("plain", "modular") or batch_size < 2:
+            return False
+        if not (batch_size <= agent.fused_max_batch or FusedLearner.use_tc(agent, batch_size)):
             return False
         named = list(agent.act.named_parameters()) + list(agent.cri.named_parameters())
         return all(p.requires_grad or n == "priorK" for n, p in named) and agent.act.a_std_log.numel() == 1
@@ -298,6 +307,40 @@ class FusedLearner:
         if self.grad is None:
             self.grad = torch.zeros_like(self.theta)
         return self.grad
+
+    def step_tc(self, data, idx, agent, distributed=False):
+        """One minibatch step on the tensor cores: pime_ppo_grad_tc -> (all-reduce) -> pime_ppo_apply_grad -> close."""
+        C, L = self.C, self.L
+        B = int(idx.numel())
+        grad = self.dist_grad()
+        key = ("tc", tuple(t.data_ptr() for t in data), B)
+        if self._args is None or self._args[0] != key:
+            state, action, r_sum, logprob, advantage = data
+            need = int(L.lib().pime_ppo_tc_work_bytes(C.byref(self.cfg), C.c_int32(B)))
+            if need < 0:
+                raise ValueError("the tensor-core learner needs net_dim 128 or 256")
+            if self.work_tc is None or self.work_tc.numel() < need:
+                self.work_tc = torch.empty(need, dtype=torch.uint8, device=self.device)
+            grp = agent.optimizer.param_groups[0]
+            a = L.PpoArgs(actor=C.pointer(self.cfg), theta=L.ptr(self.theta), theta_t=L.ptr(self.theta_t), adam_m=L.ptr(self.m),
+                          adam_v=L.ptr(self.v), grad_out=None, buf_state=L.ptr(state), buf_action=L.ptr(action),
+                          buf_r_sum=L.ptr(r_sum), buf_logprob=L.ptr(logprob), buf_advantage=L.ptr(advantage), batch=B,
+                          ratio_clip=agent.ratio_clip, lambda_entropy=agent.lambda_entropy, lr=grp["lr"],
+                          beta1=grp["betas"][0], beta2=grp["betas"][1], eps=grp["eps"], state=L.ptr(self.state),
+                          work=None, loss_ring=L.ptr(self.loss_ring), ring_len=self.RING)
+            self._args = (key, a, C.byref(a), data)
+        a = self._args[1]
+        a.idx = idx.data_ptr()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        lib = L.lib()
+        L.check(lib.pime_ppo_grad_tc(self._args[2], L.ptr(self.work_tc), L.ptr(grad), stream))
+        scale = 1.0
+        if distributed:
+            torch.distributed.all_reduce(grad)
+            scale = 1.0 / torch.distributed.get_world_size()
+        L.check(lib.pime_ppo_apply_grad(self._args[2], L.ptr(grad), C.c_float(scale), stream))
+        L.check(lib.pime_ppo_close_step(self._args[2], stream))
+        self.steps += 1
 
     def losses(self, first, count):
         """Rows [first, first + count) of the loss ring -> [count, 4] (united, actor, critic, entropy)."""
@@ -404,7 +447,8 @@ class AgentPPO:
         self.graph_max_batch = 8192
         self.graph_steps = 4            # minibatch steps per recorded graph
         self.use_fused_learner = True   # pime_ppo_step (two launches per minibatch) when FusedLearner.eligible
-        self.fused_max_batch = 4096     # beyond it the cuBLAS autograd step is faster than the fp32 SIMT kernels
+        self.fused_max_batch = 4096     # the fp32 SIMT kernels (pime_ppo_step) up to here
+        self.tc_learner_min_batch = 2048  # from here on the tcgen05 step (pime_ppo_grad_tc) when net_dim is 128 or 256
         self._fused = None
         self.learner_path = None        # which minibatch step the last update_net ran (reported by bench.py)
         self.value_fp32_max_rows = 1 << 20
@@ -634,13 +678,21 @@ class AgentPPO:
         f.load(self.act, self.cri)
         data = (data[0].contiguous(),) + tuple(t.reshape(-1).contiguous() for t in data[1:])   # [L, S], then four [L] columns
         first = f.steps
-        grad = f.dist_grad() if _dist_on() else None
-        for _ in range(iters):
-            idx = torch.randint(buf_len, size=(batch_size,), device=self.device)
-            f.step(data, idx, self, grad)
+        dist_on = _dist_on()
+        if FusedLearner.use_tc(self, batch_size):
+            for _ in range(iters):
+                idx = torch.randint(buf_len, size=(batch_size,), device=self.device)
+                f.step_tc(data, idx, self, dist_on)
+            self.learner_path = ("pime_ppo_grad_tc (tcgen05: 128-row tiles, fp16 hi/lo operands, fp32 accumulation in TMEM) -> " +
+                                 ("NCCL all-reduce of the flat gradient -> " if dist_on else "") + "pime_ppo_apply_grad (Adam)")
+        else:
+            grad = f.dist_grad() if dist_on else None
+            for _ in range(iters):
+                idx = torch.randint(buf_len, size=(batch_size,), device=self.device)
+                f.step(data, idx, self, grad)
+            self.learner_path = ("pime_ppo_step (rows + weight-gradient kernels, fp32" +
+                                 (", NCCL all-reduce of the flat gradient, Adam kernel)" if grad is not None else ", Adam fused)"))
         f.store(self.act, self.cri)
-        self.learner_path = ("pime_ppo_step (rows + weight-gradient kernels, fp32" +
-                             (", NCCL all-reduce of the flat gradient, Adam kernel)" if grad is not None else ", Adam fused)"))
         f._args = None                      # do not keep the replay tensors alive between calls
         self._n_updates += int(repeat_times)
         keep = min(iters, f.RING - 1)

@@ -164,7 +164,9 @@ def test_pack_block_list_matches_the_kernels_static_mma_program(L, kind, S, H):
     assert got == _device_program(kind, H, S)
     sizes = [buf[4 * b + 3] for b in range(n)]
     assert all(0 < s <= 16384 and s == N * k * 32 for s, (N, k, _) in zip(sizes, got))
-    assert sum(sizes) + 4096 == L.lib().pime_actor_pack_bytes(C.byref(cfg))
+    # header + fp16 blocks, then the fp32 copy of the parameters (the fidelity-mode forward reads it), both 16-byte aligned
+    f32_off = (sum(sizes) + 4096 + 15) & ~15
+    assert ((f32_off + 4 * L.lib().pime_actor_param_count(C.byref(cfg)) + 15) & ~15) == L.lib().pime_actor_pack_bytes(C.byref(cfg))
     assert all(d + N <= 2 * H for N, _, d in got)              # accumulators stay inside the two TMEM buffers
 
 
