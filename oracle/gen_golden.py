@@ -456,7 +456,9 @@ def gen_last_state(ref):
     out["wt_rows"] = np.asarray(rows, np.float64)
     out["wt_script"] = np.asarray(script, np.float64)
 
+    np.random.seed(4243)                                  # sample_parameters draws from numpy's global stream
     env = ref.gym.make(PH_INT, reset_from_last_state=True)
+    env.seed(4243)                                        # x0 / r draws come from the env's own np_random (ph.py:124,420-424)
     u = env.unwrapped
     rows, script = [], []
 

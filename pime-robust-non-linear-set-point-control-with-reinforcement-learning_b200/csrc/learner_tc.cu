@@ -63,6 +63,41 @@ __device__ __forceinline__ void join8(const uint4 &hi, const uint4 &lo, float (&
 }
 __device__ __forceinline__ float act_grad(int act, float a) { return act == ACT_TANH ? 1.0f - a * a : (a > 0.0f ? 1.0f : 0.0f); }
 
+// tanh to ~3e-7 absolute without the slow branches of tanhf: 1 - 2 / (1 + e^{2x}) with ex2.approx (2^-22 relative) and a
+// correctly rounded division; the clamp keeps e^{2x} finite.  (The rollout engine's tanh.approx.f32, 5e-4, is too coarse
+// for fp32-grade gradients.)
+__device__ __forceinline__ float tanh_acc(float x) {
+    const float t = __expf(2.0f * fminf(fmaxf(x, -15.0f), 15.0f));
+    return 1.0f - __fdiv_rn(2.0f, t + 1.0f);
+}
+
+// Column sums of a [32 lanes][N values] register tile in N - 1 + (32 / N >= 1 ? log2(32 / N) : 0) shuffles: at every stage a
+// lane keeps one half of its values and receives the partner's copy of that half ("transpose-reduce").  Returns, in lane l,
+// the sum over the 32 lanes of column col_of(l); for N = 8 four lanes hold each column after three stages and two plain
+// butterfly stages finish the sum (every lane of a group of four then holds the same total).
+template <int N> __device__ __forceinline__ float colsum(float (&v)[N], int lane, int &col) {
+    static_assert(N == 8 || N == 32, "tile width");
+    int base = 0;
+#pragma unroll
+    for (int w = N / 2, o = 16; w >= 1; w >>= 1, o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const float keep = upper ? v[i + w] : v[i];
+            const float send = upper ? v[i] : v[i + w];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+        base += upper ? w : 0;
+    }
+    float s = v[0];
+    if (N == 8) {
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+    }
+    col = base;
+    return s;
+}
+
 // instruction descriptor kind::f16, D = f32, A = B = f16; MAJOR = 1: both operands MN-major (bits 15, 16)
 __host__ __device__ constexpr uint32_t idesc(int M, int N, int mn_major) {
     return tc::make_idesc(M, N) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u);
@@ -89,12 +124,15 @@ struct GemmBatch {
     int n, row_tiles;
 };
 
-constexpr int kGemmStages = 3;
+#ifndef PIME_TC_GEMM_STAGES
+#define PIME_TC_GEMM_STAGES 1
+#endif
+constexpr int kGemmStages = PIME_TC_GEMM_STAGES;   // 1: 65 KB per CTA, three CTAs per SM overlap one another's load / MMA / epilogue phases
 constexpr int kGemmStage = 4 * kBlk;                      // A_hi, A_lo, W_hi, W_lo
 constexpr int kGemmSmem = kGemmStages * kGemmStage + 1024;
-constexpr int kGemmThreads = 192;                         // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue (one thread per row)
+constexpr int kGemmThreads = 320;                         // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue (two threads per row: column halves)
 
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_kk_kernel(const __grid_constant__ GemmBatch gb) {
+__global__ void __launch_bounds__(kGemmThreads, kGemmStages == 1 ? 3 : 1) gemm_kk_kernel(const __grid_constant__ GemmBatch gb) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const GemmProb &P = gb.p[blockIdx.z];
     const int nt = blockIdx.x, rt = blockIdx.y;
@@ -163,47 +201,57 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_kk_kernel(const __grid_c
     } else {
         mbar_wait(acc_ready, 0);
         tc_fence_after();
-        const int row = 32 * (warp & 3) + lane;
+        const int row = 32 * (warp & 3) + lane;          // TMEM lane quarter = warp % 4; warps 2-5 / 6-9 take the two column halves
+        const int half = (warp - 2) >> 2;
         const uint32_t taddr = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-        for (int j = 0; j < P.n_cols / 32; ++j) {
+        const int jn = P.n_cols / 64;                     // 32-column pieces per half
+        for (int j = half * jn; j < (half + 1) * jn; ++j) {
             float v[32];
             tmem_ld32(taddr + j * 32, v);
+            if (P.mode == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int col = j * 32 + q * 8;                 // column inside the tile
-                const int unit = nt * 128 + col;                // output unit inside the problem
-                float x[8];
-                if (P.mode == 0) {
+                for (int q = 0; q < 4; ++q) {
+                    const int unit = nt * 128 + j * 32 + q * 8;     // output unit inside the problem
+                    float x[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const float z = v[q * 8 + e] + (P.bias ? __ldg(P.bias + unit + e) : 0.0f);
-                        x[e] = P.act == ACT_TANH ? tanhf(z) : fmaxf(z, 0.0f);
+                        x[e] = P.act == ACT_TANH ? tanh_acc(z) : fmaxf(z, 0.0f);
                     }
-                } else {
-                    const int pu = P.ap_c0 * 64 + unit;
-                    const size_t o = (size_t)(((pu & 63) >> 3) * 128 + row) * 16;
-                    const uint4 ah = *reinterpret_cast<const uint4 *>(P.APREV + tblock(rt, P.ap_chunks, pu >> 6, 0) + o);
-                    const uint4 al = *reinterpret_cast<const uint4 *>(P.APREV + tblock(rt, P.ap_chunks, pu >> 6, 1) + o);
-                    float a[8];
-                    join8(ah, al, a);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] = v[q * 8 + e] * act_grad(P.act, a[e]);
-                    if (P.db) {   // bias gradient of the producing layer: column sums over the 32 rows of this warp
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float s = x[e];
-#pragma unroll
-                            for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
-                            if (lane == 0) atomicAdd(&s_db[col + e], s);
-                        }
-                    }
+                    uint4 hi, lo;
+                    split8(x, hi, lo);
+                    const int ou = P.out_c0 * 64 + unit;
+                    const size_t o = (size_t)(((ou & 63) >> 3) * 128 + row) * 16;
+                    *reinterpret_cast<uint4 *>(P.OUT + tblock(rt, P.out_chunks, ou >> 6, 0) + o) = hi;
+                    *reinterpret_cast<uint4 *>(P.OUT + tblock(rt, P.out_chunks, ou >> 6, 1) + o) = lo;
                 }
-                uint4 hi, lo;
-                split8(x, hi, lo);
-                const int ou = P.out_c0 * 64 + unit;
-                const size_t o = (size_t)(((ou & 63) >> 3) * 128 + row) * 16;
-                *reinterpret_cast<uint4 *>(P.OUT + tblock(rt, P.out_chunks, ou >> 6, 0) + o) = hi;
-                *reinterpret_cast<uint4 *>(P.OUT + tblock(rt, P.out_chunks, ou >> 6, 1) + o) = lo;
+            } else {
+                uint4 ah[4], al[4];                       // the four 8-unit groups of the activation: loads in flight together
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int pu = P.ap_c0 * 64 + nt * 128 + j * 32 + q * 8;
+                    const size_t o = (size_t)(((pu & 63) >> 3) * 128 + row) * 16;
+                    ah[q] = *reinterpret_cast<const uint4 *>(P.APREV + tblock(rt, P.ap_chunks, pu >> 6, 0) + o);
+                    al[q] = *reinterpret_cast<const uint4 *>(P.APREV + tblock(rt, P.ap_chunks, pu >> 6, 1) + o);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float a[8], x[8];
+                    join8(ah[q], al[q], a);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { x[e] = v[q * 8 + e] * act_grad(P.act, a[e]); v[q * 8 + e] = x[e]; }
+                    uint4 hi, lo;
+                    split8(x, hi, lo);
+                    const int ou = P.out_c0 * 64 + nt * 128 + j * 32 + q * 8;
+                    const size_t o = (size_t)(((ou & 63) >> 3) * 128 + row) * 16;
+                    *reinterpret_cast<uint4 *>(P.OUT + tblock(rt, P.out_chunks, ou >> 6, 0) + o) = hi;
+                    *reinterpret_cast<uint4 *>(P.OUT + tblock(rt, P.out_chunks, ou >> 6, 1) + o) = lo;
+                }
+                if (P.db) {   // bias gradient of the producing layer: column sums over this warp's 32 rows, one column per lane
+                    int col;
+                    const float s_ = colsum<32>(v, lane, col);
+                    atomicAdd(&s_db[j * 32 + col], s_);
+                }
             }
         }
         tc_fence_before();
@@ -520,16 +568,16 @@ __global__ void __launch_bounds__(256) out_obj_kernel(const StepCommon c, const 
 #pragma unroll
         for (int e = 0; e < 8; ++e) x[e] = fminf(fmaxf(ds * __ldg(w + ug * 8 + e) * act_grad(N.act, a[e]), -6e4f), 6e4f);
         uint4 hi, lo;
-        split8(x, hi, lo);
+        split8(x, hi, lo);   // (colsum below consumes x)
         *reinterpret_cast<uint4 *>(N.DZ + tblock(rt, N.chunks, ug >> 3, 0) + o) = hi;
         *reinterpret_cast<uint4 *>(N.DZ + tblock(rt, N.chunks, ug >> 3, 1) + o) = lo;
+        float s8[8];                    // lanes = 32 consecutive rows of the same unit group: column sums over the rows
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {   // lanes = 32 consecutive rows of the same unit group
-            float s = d * a[e], sb = x[e];
-#pragma unroll
-            for (int o2 = 16; o2 > 0; o2 >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o2); sb += __shfl_xor_sync(0xffffffffu, sb, o2); }
-            if (lane == 0) { atomicAdd(&gw[ug * 8 + e], s); atomicAdd(&gb_last[ug * 8 + e], sb); }
-        }
+        for (int e = 0; e < 8; ++e) s8[e] = d * a[e];
+        int col;
+        const float sw = colsum<8>(s8, lane, col);
+        const float sb = colsum<8>(x, lane, col);
+        if ((lane & 3) == 0) { atomicAdd(&gw[ug * 8 + col], sw); atomicAdd(&gb_last[ug * 8 + col], sb); }
     }
     __syncthreads();
     const float unscale = 1.0f / c.dz_scale[net];
