@@ -44,12 +44,19 @@ __host__ __device__ __forceinline__ size_t tblock(int row_tile, int chunks, int 
     return ((size_t)((size_t)row_tile * chunks + chunk) * 2 + hl) * kBlk;
 }
 
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): pairs of values through the packed conversions
 __device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi, uint4 &lo) {
-    __half h[8], l[8];
+    uint32_t h[4], l[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) tc::split_h(x[e], h[e], l[e]);
-    hi = make_uint4(tc::pack_hh(h[0], h[1]), tc::pack_hh(h[2], h[3]), tc::pack_hh(h[4], h[5]), tc::pack_hh(h[6], h[7]));
-    lo = make_uint4(tc::pack_hh(l[0], l[1]), tc::pack_hh(l[2], l[3]), tc::pack_hh(l[4], l[5]), tc::pack_hh(l[6], l[7]));
+    for (int q = 0; q < 4; ++q) {
+        const __half2 hh = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+        const float2 back = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(x[2 * q] - back.x, x[2 * q + 1] - back.y);
+        h[q] = *reinterpret_cast<const uint32_t *>(&hh);
+        l[q] = *reinterpret_cast<const uint32_t *>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 __device__ __forceinline__ void join8(const uint4 &hi, const uint4 &lo, float (&x)[8]) {
     const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
@@ -63,12 +70,15 @@ __device__ __forceinline__ void join8(const uint4 &hi, const uint4 &lo, float (&
 }
 __device__ __forceinline__ float act_grad(int act, float a) { return act == ACT_TANH ? 1.0f - a * a : (a > 0.0f ? 1.0f : 0.0f); }
 
-// tanh to ~3e-7 absolute without the slow branches of tanhf: 1 - 2 / (1 + e^{2x}) with ex2.approx (2^-22 relative) and a
-// correctly rounded division; the clamp keeps e^{2x} finite.  (The rollout engine's tanh.approx.f32, 5e-4, is too coarse
-// for fp32-grade gradients.)
+// tanh to ~4e-7 absolute without the slow branches of tanhf: 1 - 2 / (1 + e^{2x}) = 1 - 2 rcp(1 + ex2(2 log2(e) x)) with
+// ex2.approx / rcp.approx (2^-22, 1 ulp); the clamp keeps e^{2x} finite.  7 instructions, 2 of them MUFU.  (The rollout
+// engine's tanh.approx.f32, 5e-4, is too coarse for fp32-grade gradients.)
 __device__ __forceinline__ float tanh_acc(float x) {
-    const float t = __expf(2.0f * fminf(fmaxf(x, -15.0f), 15.0f));
-    return 1.0f - __fdiv_rn(2.0f, t + 1.0f);
+    float t, r;
+    const float y = 2.8853900817779268f * fminf(fmaxf(x, -15.0f), 15.0f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(y));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
 }
 
 // Column sums of a [32 lanes][N values] register tile in N - 1 + (32 / N >= 1 ? log2(32 / N) : 0) shuffles: at every stage a
@@ -123,6 +133,67 @@ struct GemmBatch {
     GemmProb p[kMaxProb];
     int n, row_tiles;
 };
+
+// One 32-column piece of a GEMM epilogue for the row of this thread: forward (bias + activation) or data gradient
+// (x act'(stored activation)), hi / lo split, T-format stores.  Data gradient: returns, in lane l, the sum over the warp's 32
+// rows of column l of the piece (the bias gradient of the producing layer).
+__device__ __forceinline__ float epi_piece(const GemmProb &P, int rt, int nt, int j, int row, int lane, float (&v)[32]) {
+    if (P.mode == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int unit = nt * 128 + j * 32 + q * 8;     // output unit inside the problem
+            float x[8], bz[8];
+            if (P.bias) {   // every bias vector starts on a 16-byte boundary of theta? not guaranteed: scalar loads unless aligned
+                if ((reinterpret_cast<uintptr_t>(P.bias + unit) & 15) == 0) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(P.bias + unit)), b1 = __ldg(reinterpret_cast<const float4 *>(P.bias + unit) + 1);
+                    bz[0] = b0.x; bz[1] = b0.y; bz[2] = b0.z; bz[3] = b0.w; bz[4] = b1.x; bz[5] = b1.y; bz[6] = b1.z; bz[7] = b1.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) bz[e] = __ldg(P.bias + unit + e);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bz[e] = 0.0f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float z = v[q * 8 + e] + bz[e];
+                x[e] = P.act == ACT_TANH ? tanh_acc(z) : fmaxf(z, 0.0f);
+            }
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            const int ou = P.out_c0 * 64 + unit;
+            const size_t o = (size_t)(((ou & 63) >> 3) * 128 + row) * 16;
+            *reinterpret_cast<uint4 *>(P.OUT + tblock(rt, P.out_chunks, ou >> 6, 0) + o) = hi;
+            *reinterpret_cast<uint4 *>(P.OUT + tblock(rt, P.out_chunks, ou >> 6, 1) + o) = lo;
+        }
+        return 0.0f;
+    }
+    uint4 ah[4], al[4];                       // the four 8-unit groups of the activation: loads in flight together
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int pu = P.ap_c0 * 64 + nt * 128 + j * 32 + q * 8;
+        const size_t o = (size_t)(((pu & 63) >> 3) * 128 + row) * 16;
+        ah[q] = *reinterpret_cast<const uint4 *>(P.APREV + tblock(rt, P.ap_chunks, pu >> 6, 0) + o);
+        al[q] = *reinterpret_cast<const uint4 *>(P.APREV + tblock(rt, P.ap_chunks, pu >> 6, 1) + o);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float a[8], x[8];
+        join8(ah[q], al[q], a);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { x[e] = v[q * 8 + e] * act_grad(P.act, a[e]); v[q * 8 + e] = x[e]; }
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const int ou = P.out_c0 * 64 + nt * 128 + j * 32 + q * 8;
+        const size_t o = (size_t)(((ou & 63) >> 3) * 128 + row) * 16;
+        *reinterpret_cast<uint4 *>(P.OUT + tblock(rt, P.out_chunks, ou >> 6, 0) + o) = hi;
+        *reinterpret_cast<uint4 *>(P.OUT + tblock(rt, P.out_chunks, ou >> 6, 1) + o) = lo;
+    }
+    if (!P.db) return 0.0f;
+    int col;
+    return colsum<32>(v, lane, col);          // col == lane
+}
 
 #ifndef PIME_TC_GEMM_STAGES
 #define PIME_TC_GEMM_STAGES 1
@@ -208,51 +279,8 @@ __global__ void __launch_bounds__(kGemmThreads, kGemmStages == 1 ? 3 : 1) gemm_k
         for (int j = half * jn; j < (half + 1) * jn; ++j) {
             float v[32];
             tmem_ld32(taddr + j * 32, v);
-            if (P.mode == 0) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int unit = nt * 128 + j * 32 + q * 8;     // output unit inside the problem
-                    float x[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float z = v[q * 8 + e] + (P.bias ? __ldg(P.bias + unit + e) : 0.0f);
-                        x[e] = P.act == ACT_TANH ? tanh_acc(z) : fmaxf(z, 0.0f);
-                    }
-                    uint4 hi, lo;
-                    split8(x, hi, lo);
-                    const int ou = P.out_c0 * 64 + unit;
-                    const size_t o = (size_t)(((ou & 63) >> 3) * 128 + row) * 16;
-                    *reinterpret_cast<uint4 *>(P.OUT + tblock(rt, P.out_chunks, ou >> 6, 0) + o) = hi;
-                    *reinterpret_cast<uint4 *>(P.OUT + tblock(rt, P.out_chunks, ou >> 6, 1) + o) = lo;
-                }
-            } else {
-                uint4 ah[4], al[4];                       // the four 8-unit groups of the activation: loads in flight together
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int pu = P.ap_c0 * 64 + nt * 128 + j * 32 + q * 8;
-                    const size_t o = (size_t)(((pu & 63) >> 3) * 128 + row) * 16;
-                    ah[q] = *reinterpret_cast<const uint4 *>(P.APREV + tblock(rt, P.ap_chunks, pu >> 6, 0) + o);
-                    al[q] = *reinterpret_cast<const uint4 *>(P.APREV + tblock(rt, P.ap_chunks, pu >> 6, 1) + o);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float a[8], x[8];
-                    join8(ah[q], al[q], a);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) { x[e] = v[q * 8 + e] * act_grad(P.act, a[e]); v[q * 8 + e] = x[e]; }
-                    uint4 hi, lo;
-                    split8(x, hi, lo);
-                    const int ou = P.out_c0 * 64 + nt * 128 + j * 32 + q * 8;
-                    const size_t o = (size_t)(((ou & 63) >> 3) * 128 + row) * 16;
-                    *reinterpret_cast<uint4 *>(P.OUT + tblock(rt, P.out_chunks, ou >> 6, 0) + o) = hi;
-                    *reinterpret_cast<uint4 *>(P.OUT + tblock(rt, P.out_chunks, ou >> 6, 1) + o) = lo;
-                }
-                if (P.db) {   // bias gradient of the producing layer: column sums over this warp's 32 rows, one column per lane
-                    int col;
-                    const float s_ = colsum<32>(v, lane, col);
-                    atomicAdd(&s_db[j * 32 + col], s_);
-                }
-            }
+            const float cs = epi_piece(P, rt, nt, j, row, lane, v);
+            if (P.mode == 1 && P.db) atomicAdd(&s_db[j * 32 + lane], cs);
         }
         tc_fence_before();
     }
@@ -264,6 +292,7 @@ __global__ void __launch_bounds__(kGemmThreads, kGemmStages == 1 ? 3 : 1) gemm_k
     if (warp == 1) tc_fence_after();
     if (warp == 1) tmem_dealloc(tmem, 128);
 }
+
 
 // ------------------------------------------------------------------------------------------------ weight-gradient GEMM
 // G[m][n] = sum over the batch rows of MOP[row][m] * NOP[row][n]: both operands MN-major (units = M / N of the MMA, rows = K),
