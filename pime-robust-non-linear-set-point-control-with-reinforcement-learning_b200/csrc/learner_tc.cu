@@ -312,21 +312,25 @@ struct WgBatch {
     int n, row_tiles;
     float *grad;
 };
-constexpr int kWgSmem = 8 * kBlk + 1024;
+constexpr int kWgSmem = 12 * kBlk + 1024;   // two hi buffers (M_hi 2 blocks + N_hi 2 blocks) + one lo buffer
 constexpr int kWgThreads = 192;
 
+// Shared memory: H[0], H[1] (the hi blocks of row tile i, i + 1: 64 KB each) and L (the lo blocks of row tile i: 64 KB).  A row
+// tile's products are  M_hi N_hi  (needs H only)  then  M_lo N_hi + M_hi N_lo  (needs L too): while those run, the hi blocks
+// of the next row tile are already landing in the other H buffer, and its lo blocks follow as soon as L is released.
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_mn_kernel(const __grid_constant__ WgBatch wb) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const WgProb &P = wb.p[blockIdx.z];
     if ((int)blockIdx.x >= P.m_tiles * P.n_tiles) return;
     const int mt = blockIdx.x / P.n_tiles, ntile = blockIdx.x % P.n_tiles;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + 8 * kBlk);
-    uint64_t *empty = full + 1;
-    uint64_t *acc_ready = empty + 1;
+    uint64_t *h_full = reinterpret_cast<uint64_t *>(smem + 12 * kBlk);   // [2]
+    uint64_t *h_empty = h_full + 2;                                      // [2]
+    uint64_t *l_full = h_empty + 2, *l_empty = l_full + 1, *acc_ready = l_empty + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_ready + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        mbar_init(full, 1); mbar_init(empty, 1); mbar_init(acc_ready, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&h_full[b], 1); mbar_init(&h_empty[b], 1); }
+        mbar_init(l_full, 1); mbar_init(l_empty, 1); mbar_init(acc_ready, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 128);
@@ -336,46 +340,53 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_mn_kernel(const __grid_co
     const uint32_t tmem = *tmem_slot;
     const int my_tiles = (wb.row_tiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
     const int nblk = P.n_cols == 128 ? 2 : 1;            // chunks of the N operand per tile
-    // shared memory: M_hi (2 blocks) | M_lo (2 blocks) | N_hi (nblk blocks) | N_lo (nblk blocks)
+    uint8_t *sL = smem + 8 * kBlk;
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t ph = 0;
             for (int i = 0; i < my_tiles; ++i) {
                 const int rt = blockIdx.y + i * gridDim.y;
-                mbar_wait(empty, ph ^ 1);
-                mbar_arrive_expect_tx(full, (4 + 2 * nblk) * kBlk);
+                const uint32_t buf = (uint32_t)i & 1u;
+                uint8_t *sH = smem + buf * 4 * kBlk;
                 for (int hl = 0; hl < 2; ++hl) {
-                    for (int c = 0; c < 2; ++c)
-                        bulk_g2s(smem + (2 * hl + c) * kBlk, P.MOP + tblock(rt, P.m_chunks, P.m_c0 + 2 * mt + c, hl), kBlk, full);
+                    uint64_t *bar = hl == 0 ? &h_full[buf] : l_full;
+                    uint8_t *dst = hl == 0 ? sH : sL;
+                    if (hl == 0) mbar_wait(&h_empty[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);
+                    else mbar_wait(l_empty, ((uint32_t)i & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(bar, (2 + nblk) * kBlk);
+                    for (int c = 0; c < 2; ++c) bulk_g2s(dst + c * kBlk, P.MOP + tblock(rt, P.m_chunks, P.m_c0 + 2 * mt + c, hl), kBlk, bar);
                     for (int c = 0; c < nblk; ++c)
-                        bulk_g2s(smem + (4 + nblk * hl + c) * kBlk, P.NOP + tblock(rt, P.n_chunks, P.n_c0 + nblk * ntile + c, hl), kBlk, full);
+                        bulk_g2s(dst + (2 + c) * kBlk, P.NOP + tblock(rt, P.n_chunks, P.n_c0 + nblk * ntile + c, hl), kBlk, bar);
                 }
-                ph ^= 1;
             }
         }
     } else if (warp == 1) {
-        uint32_t ph = 0;
         const uint32_t id = P.n_cols == 128 ? idesc(128, 128, 1) : idesc(128, 64, 1);
         for (int i = 0; i < my_tiles; ++i) {
-            mbar_wait(full, ph);
+            const uint32_t buf = (uint32_t)i & 1u;
+            const uint32_t hb = smem_u32(smem) + buf * 4 * kBlk, lb = smem_u32(sL);
+            // MN-major, no swizzle: K groups (8 rows) 128 B apart (LBO), MN groups (8 units) one unit group apart (SBO);
+            // 16 batch rows per MMA = 256 B further into every unit group
+            mbar_wait(&h_full[buf], ((uint32_t)i >> 1) & 1u);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t base = smem_u32(smem);
 #pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {   // 16 batch rows per MMA: 256 B further into every unit group
-                    // MN-major, no swizzle: K groups (8 rows) 128 B apart (LBO), MN groups (8 units) one unit group apart (SBO)
-                    const uint64_t m_hi = make_desc(base + kk * 256, 128, kUg), m_lo = make_desc(base + 2 * kBlk + kk * 256, 128, kUg);
-                    const uint64_t n_hi = make_desc(base + 4 * kBlk + kk * 256, 128, kUg);
-                    const uint64_t n_lo = make_desc(base + (4 + nblk) * kBlk + kk * 256, 128, kUg);
-                    mma_f16(tmem, m_hi, n_hi, id, (i == 0 && kk == 0) ? 0u : 1u);
-                    mma_f16(tmem, m_lo, n_hi, id, 1u);
-                    mma_f16(tmem, m_hi, n_lo, id, 1u);
+                for (int kk = 0; kk < 8; ++kk)
+                    mma_f16(tmem, make_desc(hb + kk * 256, 128, kUg), make_desc(hb + 2 * kBlk + kk * 256, 128, kUg), id, (i == 0 && kk == 0) ? 0u : 1u);
+            }
+            __syncwarp();
+            mbar_wait(l_full, (uint32_t)i & 1u);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    mma_f16(tmem, make_desc(lb + kk * 256, 128, kUg), make_desc(hb + 2 * kBlk + kk * 256, 128, kUg), id, 1u);   // M_lo N_hi
+                    mma_f16(tmem, make_desc(hb + kk * 256, 128, kUg), make_desc(lb + 2 * kBlk + kk * 256, 128, kUg), id, 1u);   // M_hi N_lo
                 }
-                mma_commit(empty);
+                mma_commit(l_empty);
+                mma_commit(&h_empty[buf]);
                 if (i == my_tiles - 1) mma_commit(acc_ready);
             }
             __syncwarp();
-            ph ^= 1;
         }
     } else if (my_tiles > 0) {
         mbar_wait(acc_ready, 0);
