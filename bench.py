@@ -162,6 +162,17 @@ def resolve(args, world=1):
     return w
 
 
+def base_config(args, w):
+    """The `config` object of the JSON line -- the same keys and values for the b200 arm and the reference arm."""
+    n, T, S = w["n"], w["T"], w["S"]
+    return {"workload": w["name"], "envs_per_gpu": n, "T": T, "actor": w["actor"], "env": w["env"],
+            "noise_scale": 0.0 if args.workload == "ph" else 0.01,
+            "policy": "stochastic (explore_env)", "replay": "GPU-resident, time-major [T,n,S]+[T,n,4] fp32",
+            "l2": f"each step streams {n * T * (S + 4) * 4 / 1e9:.2f} GB of replay rows through L2 (>> 126 MB), "
+                  "which flushes it between timed steps",
+            "sharding": "contiguous env-id ranges per rank, Philox keyed by global env id"}
+
+
 # ------------------------------------------------------------------------------------------------ CPU baseline
 def cpu_baseline(w, seconds, sd):
     """The oracle (C restatement of the reference loop: fp64 plant + fp32 actor, oracle/pime_oracle.c) on all host
@@ -198,20 +209,27 @@ def cpu_baseline(w, seconds, sd):
                 y = table[np.rint(Cc * x * 1e5).astype(np.int64)]
                 O.ph_rollout(cfg, table, acfg, params, -0.5, priorK, False, T, x, y, r, I, t, A, B, Cc, eps=eps)
             counts[tid] += per * T
-    # warm-up (library load, page-in)
+    # warm-up (library load, page-in), then three samples of seconds / 3 (>= 4 s) each: the median is reported
     deadline[0] = time.perf_counter() + 0.5
     work(0)
-    counts[0] = 0
-    t0 = time.perf_counter()
-    deadline[0] = t0 + seconds
-    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
-    [x.start() for x in th]
-    [x.join() for x in th]
-    dt = time.perf_counter() - t0
-    total = sum(counts)
-    return {"value": total / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{total} env-steps ({total // T} episodes of T={T}, {'WT' if is_wt else 'pH'}-Integrator + Modular-{H} actor, "
-                      f"fp64 plant / fp32 actor, C oracle, {cores} threads) in {dt:.1f} s"}
+    rates, totals, dts = [], [], []
+    per_sample = max(seconds / 3.0, 4.0) if seconds >= 6.0 else seconds
+    for _ in range(3 if seconds >= 6.0 else 1):
+        for i in range(cores):
+            counts[i] = 0
+        t0 = time.perf_counter()
+        deadline[0] = t0 + per_sample
+        th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+        [x.start() for x in th]
+        [x.join() for x in th]
+        dts.append(time.perf_counter() - t0)
+        totals.append(sum(counts))
+        rates.append(totals[-1] / dts[-1])
+    k = int(np.argsort(rates)[len(rates) // 2])
+    total, dt = totals[k], dts[k]
+    return {"value": rates[k], "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"median of {len(rates)} samples; this one: {total} env-steps ({total // T} episodes of T={T}, {'WT' if is_wt else 'pH'}-Integrator + "
+                      f"Modular-{H} actor, fp64 plant / fp32 actor, C oracle, {cores} threads) in {dt:.1f} s"}
 
 
 def run_reference(args):
@@ -228,16 +246,16 @@ def run_reference(args):
     for _ in range(max(1, args.steps)):
         last = cpu_baseline(w, max(2.0, min(args.cpu_seconds, 60.0 / max(1, args.steps))), sd)
         vals.append(last["value"])
-    v = float(np.mean(vals))
+    v = float(np.median(vals))
     last["value"] = v
     per_step_envsteps = v * (time.perf_counter() - t0) / max(1, args.steps)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * (time.perf_counter() - t0) / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 plant / f32 actor",
             "data": "synthetic",
-            "config": {"workload": w["name"], "envs_per_gpu": w["n"], "T": w["T"], "actor": w["actor"],
-                       "note": "reference algorithm (C port of the numpy/torch loop) on all host cores; each step is a bounded "
-                               f"sample (~{per_step_envsteps:.3g} env-steps) of the workload"},
+            "config": base_config(args, w),
+            "note": "reference algorithm (C port of the numpy/torch loop) on all host cores; each step is a bounded "
+                    f"sample (~{per_step_envsteps:.3g} env-steps) of the workload; value = median over the steps",
             "cpu_baseline": last,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -382,12 +400,7 @@ def run_b200(args):
             "scaling": "strong" if (args.workload == "ph" and not args.envs) else "weak", "vs_baseline": None,
             "dtype": "f32 (plant, prior, obs, first and last actor layer; hidden layers: f16 tensor-core operands, f32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": w["name"], "envs_per_gpu": n, "T": T, "actor": w["actor"], "env": w["env"],
-                       "noise_scale": 0.0 if args.workload == "ph" else 0.01,
-                       "policy": "stochastic (explore_env)", "replay": "GPU-resident, time-major [T,n,S]+[T,n,4] fp32",
-                       "l2": f"each step streams {(bs.numel() + bo.numel()) * 4 / 1e9:.2f} GB of replay rows through L2 (>> 126 MB), "
-                             "which flushes it between timed steps",
-                       "sharding": "contiguous env-id ranges per rank, Philox keyed by global env id"},
+            "config": base_config(args, w),
             "clocks": clocks, "gpu_launches": args.steps,
             "episode_stats": {"mean_return": st[0] / max(st[2], 1), "episodes": st[2]}}
     if e2e:
@@ -478,6 +491,20 @@ def extra_config4(V, world, rank, dist, barrier, pk, steps=5, warmup=2):
     return out
 
 
+LEARNER_FLOP_PER_ROW = 2 * 3 * (132352 + 133121)   # forward + data gradient + weight gradient of Modular-256 + CriticAdv-256, 2 FLOP per weight
+
+
+def learner_roofline(buf_len, batch, repeat, update_ms):
+    """Tensor-pipe view of the update: algorithmic FLOPs of the minibatch steps (x3 issued: hi/lo terms) over the update time
+    (which also holds the value pass, GAE and the index draws) against the sustained bf16 peak of MEASURED_PEAKS.json."""
+    pk = peaks()
+    steps = int(repeat * buf_len / batch)
+    alg = steps * batch * LEARNER_FLOP_PER_ROW / (update_ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": alg, "issued": 3 * alg, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": alg / pk["tf_sust"],
+            "frac_issued": 3 * alg / pk["tf_sust"], "ms_per_minibatch": update_ms / max(steps, 1),
+            "note": "algorithmic = 1.59 MFLOP per minibatch row; the step issues three fp16 MMAs per product; see DESIGN.md 4.3"}
+
+
 def extra_config5(world, rank, dist, barrier, n=1 << 16, batch=1 << 17, repeat=2, iters=2):
     """BASELINE configs[4]: full residual PPO training -- explore (one fused launch into the GPU-resident replay), critic
     values + GAE kernels, repeat * T * n / batch minibatch steps with the gradient all-reduce when world > 1."""
@@ -522,8 +549,9 @@ def extra_config5(world, rank, dist, barrier, n=1 << 16, batch=1 << 17, repeat=2
             "unit": "env-steps/s", "n_gpus": world, "scaling": "weak", "workload": w["name"], "envs_per_gpu": n, "T": T,
             "actor": "ResidualIntegratorModularPPO-" + str(H), "batch_size": batch, "repeat_times": repeat,
             "minibatches_per_iteration": int(repeat * n * T / batch), "iterations": iters,
-            "learner": agent.learner_path, "dtype": "f32 learner; rollout as the headline",
-            "rollout_share": t_roll / max(t_roll + t_upd, 1e-9), "rollout_ms": 1e3 * t_roll / iters, "update_ms": 1e3 * t_upd / iters}
+            "learner": agent.learner_path, "dtype": "f32-grade learner (fp16 hi + lo operands, three MMAs per product, fp32 accumulation); rollout as the headline",
+            "rollout_share": t_roll / max(t_roll + t_upd, 1e-9), "rollout_ms": 1e3 * t_roll / iters, "update_ms": 1e3 * t_upd / iters,
+            "learner_roofline": learner_roofline(n * T, batch, repeat, 1e3 * t_upd / iters)}
 
 
 def aux_step_rooflines(V, pk):
@@ -570,7 +598,8 @@ def aux_step_rooflines(V, pk):
         out[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
                      "traffic": NCU_DRAM_BYTES_STEP.get(name),
                      "env_steps_per_s": n / (ms * 1e-3), "bytes_per_env_step": nbytes, "envs": n,
-                     "kernel": f"{name}_step_kernel<float>", "peak_source": pk["src"]}
+                     "kernel": "wt_step_vec4_kernel (4 envs per thread)" if name == "wt" else "ph_step_kernel<float> (x, A, B, index in fp64)",
+                     "peak_source": pk["src"]}
         del env
         torch.cuda.empty_cache()
     return out

@@ -48,9 +48,9 @@ def main():
     tag, launches, rollout_rep, step_rep = sys.argv[1:5]
     out = [f"# Round {tag} ncu evidence (B200, driver 580, CUDA 12.9, ncu --clock-control none)\n",
            "Commands (each after the same command exited 0 without ncu in the same gpurun call):",
-           "  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline",
-           "  ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 3 -c 1 -o ... python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-aux",
-           "  ncu --set full --clock-control none --import-source on -k regex:_step_kernel -c 2 -s 6 -o ... python bench.py --steps 2 --warmup 3 --no-cpu-baseline\n"]
+           "  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra",
+           "  ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 3 -c 1 -o ... python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra --no-aux",
+           "  ncu --set full --clock-control none --import-source on -k regex:_step_ -c 2 -s 6 -o ... python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra\n"]
     # ---- launch list
     rows = list(csv.reader(l for l in open(launches) if l.startswith('"')))
     h = rows[0]
