@@ -256,3 +256,71 @@ def test_reset_from_last_state_in_the_fused_rollout(oracle):
     ph.rollout(T, -Kp, deterministic=True, auto_reset=True)
     ph2.rollout(T, -Kp, deterministic=True, auto_reset=False)
     assert torch.equal(ph.x, ph2.x) and torch.equal(ph.last_x, ph2.x) and not torch.equal(ph.C, ph2.C)
+
+
+def test_attribute_mirrors_are_assignable_like_the_reference(G):
+    """utils/robust_test.py:12-19 writes test_env.a1 / a2 / Kp / max_step / if_reset_all on a deep copy of the env."""
+    env = G.make(WT_INT, noise_scale=0.0)
+    env.reset()
+    test_env = copy.deepcopy(env)
+    test_env.a1, test_env.a2, test_env.Kp = 0.0024, 0.0019, 0.12
+    test_env.if_reset_all = False
+    test_env.max_step = 500
+    assert (test_env.a1, test_env.a2, test_env.Kp) == (0.0024, 0.0019, 0.12) and test_env.max_step == 500
+    assert env.max_step == 200 and env.a1 != 0.0024                      # the original is untouched
+    test_env.reset()                                                     # reset_r(): the parameters stay (:935-939)
+    assert test_env.get_changable_parameters() == (0.0024, 0.0019, 0.12)
+    done = False
+    for _ in range(500):
+        _, _, done, _ = test_env.step(np.array([0.0]))
+    assert done and test_env._episode_steps == 500                       # the new step limit reached the kernels
+    test_env.h1 = 3.5
+    assert test_env.h1 == 3.5 and float(test_env.vec.h1[0]) == 3.5
+
+
+def test_stacking_set_state_leaves_the_frame_history_like_the_reference(G):
+    """nonlinear_watertank.py:205-212 are inherited unchanged by the stacking env: set_state / set_r change h1, h2, r but the
+    observation (the deque of frames, :1164-1166) only changes in reset() and step()."""
+    env = G.make("NonLinearWaterTankChangingParamUniformGoalStacking4-SquareDistance-v2", noise_scale=0.0)
+    obs0 = env.reset()
+    assert np.array_equal(obs0.reshape(4, 3), np.tile(obs0[:3], (4, 1)))   # KAT-5: every frame = the reset state
+    obs1 = env.set_state(0.0, 0.0)
+    obs1 = env.set_r(2.0)
+    assert np.array_equal(obs1, obs0) and env.h1 == 0.0 and env.r == 2.0
+    obs2, _, _, _ = env.step(np.array([0.5]))
+    assert np.array_equal(obs2[:9], obs0[3:]) and obs2[11] == 2.0 and obs2[9] > 0.0   # the new frame comes last
+
+
+def test_in_kernel_reset_honours_if_reset_all_false(G):
+    """rollout(auto_reset=True, resample_params=False) = reset_r() at every episode boundary (advisor finding, round 1)."""
+    import pime_b200.vec as V
+    env = V.WaterTankVec(512, dtype=torch.float32, seed=3)
+    env.reset()
+    p0 = [t.clone() for t in env.get_changable_parameters()]
+    r0 = env.r.clone()
+    env.rollout(450, np.array([0.0, -0.4, 0.4, 0.0]), auto_reset=True, resample_params=False)
+    assert all(torch.equal(a, b) for a, b in zip(p0, env.get_changable_parameters())) and not torch.equal(r0, env.r)
+    assert int(env.episode.min()) == 3
+    env.rollout(200, np.array([0.0, -0.4, 0.4, 0.0]), auto_reset=True)                 # default: reset_all()
+    assert not torch.equal(p0[0], env.a1)
+    ph = V.PHVec(512, dtype=torch.float32, seed=3)
+    ph.reset()
+    q0, A0 = ph.qww_V.clone(), ph.A.clone()
+    ph.rollout(120, -np.array([-0.02, 0.02, 0.035]), auto_reset=True, resample_params=False)
+    assert torch.equal(q0, ph.qww_V) and torch.equal(A0, ph.A)
+
+
+def test_device_fault_flag_accumulates_until_checked():
+    """A table overflow in an early launch must still be reported after later, clean launches (advisor finding, round 1)."""
+    import pime_b200.vec as V
+    ph = V.PHVec(64, dtype=torch.float64, seed=1)
+    ph.reset()
+    x0 = ph.x.clone()
+    ph.x.fill_(1e6); ph.A.fill_(1.0); ph.B.fill_(0.0); ph.C.fill_(0.0025)
+    K = -np.array([-0.02, 0.02, 0.035])
+    ph.rollout(2, K)                         # runs past the table
+    ph.x.copy_(x0); ph.reset()
+    ph.rollout(2, K)                         # a clean launch afterwards
+    with pytest.raises(IndexError):
+        ph.check_status()
+    ph.check_status()                        # reading the flag cleared it

@@ -79,3 +79,38 @@ def test_grid_sweep_with_an_agent_and_ph_staircase():
     assert np.all(refs[:50] == 10.0) and np.all(refs[200:] == 5.0)
     err_end = (r["ys"][49] - 10.0).abs().median()
     assert float(err_end) < 2.0                                                    # the PI prior approaches the set-point
+
+
+def test_stacking_staircase_equals_the_per_step_gym_loop():
+    """The staircase on the Stacking observation (the env of run_watertank_changing.sh): the fused launches reproduce what the
+    reference's per-step protocol (utils/test.py:70-207: reset, set_state, set_r, step ...) gives through the gym API,
+    including its quirk that set_state / set_r leave the frame history alone (the first frames of a segment are stale)."""
+    import copy
+    import pime_b200.gym_api as G
+    import pime_b200.scenarios as SC
+    env = G.make("NonLinearWaterTankChangingParamUniformGoalStacking4-SquareDistance-v2", noise_scale=0.0, seed=5)
+    env.reset()
+    env.set_reset_all(False)                       # keep the ensemble member, as utils/robust_test.py does
+    K = np.asarray(env.K, np.float64)
+    steps = 40
+    fused = SC.staircase(copy.deepcopy(env).vec, "agent", K, actor=None, setpoints=SC.WT_SETPOINTS, steps=steps, resample_params=False)
+    e2 = copy.deepcopy(env)
+    obs_l, act_l = [], []
+    e2.reset()
+    e2.set_state(0.0, 0.0)
+    for k, r in enumerate(SC.WT_SETPOINTS):
+        if k:
+            h1, h2 = e2.h1, e2.h2
+            e2.reset()
+            e2.set_state(h1, h2)
+        state = e2.set_r(r)
+        for _ in range(steps):
+            a = float(np.float32(state).astype(np.float64) @ (-K))      # the zero-residual agent: obs32 . priorK, unclipped
+            obs_l.append(state.copy()); act_l.append(a)
+            state, _, _, _ = e2.step(np.array([a]))
+    want_obs = np.asarray(obs_l, np.float32)
+    got_obs = fused["obs"][:, 0].cpu().numpy()
+    # reset() draws (h, r) from Philox keyed by the episode counter: both paths performed the same number of resets
+    np.testing.assert_allclose(got_obs, want_obs, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(fused["actions"][:, 0].cpu().numpy(), np.asarray(act_l), rtol=1e-6, atol=1e-6)
+    assert fused["xs"].shape == (5 * steps, 1, 2) and torch.equal(fused["refs"][:, 0], fused["obs"][:, 0, -1])
