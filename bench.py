@@ -47,8 +47,8 @@ WORKLOADS = {
 FLOPS_PER_STEP = {("modular", 256, 4): 264704, ("modular", 128, 3): 66560, ("plain", 256, 30): 278016}  # 2 x weights, SURVEY 8a d4/d5
 TANH_PER_STEP = {("modular", 256, 4): 1025, ("modular", 128, 3): 513, ("plain", 256, 30): 769}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (ncu --set full), keyed by (workload, envs, T); see profiles/
-NCU_DRAM_BYTES_PER_LAUNCH = {("wt", 1 << 20, 200): 6.7561e9}   # profiles/r01_ncu_summary.md (algorithmic: 6.71e9 replay rows)
-NCU_DRAM_BYTES_STEP = {"wt": 1.8720e9, "ph": 1.7354e9}   # *_step_kernel<float>, 2^25 envs (algorithmic 1.913e9 / 1.778e9)
+NCU_DRAM_BYTES_PER_LAUNCH = {("wt", 1 << 20, 200): 6.7534e9}   # profiles/r02_ncu_summary.md (algorithmic: 6.71e9 replay rows)
+NCU_DRAM_BYTES_STEP = {"wt": 1.8658e9, "ph": None}   # wt_step_vec4_kernel, 2^25 envs (algorithmic 1.913e9), profiles/r02_ncu_summary.md; pH: see the capture note there
 WT_STEP_BYTES_F32 = 57   # 36 B read + 21 B written per env-step, SoA fp32
 PH_STEP_BYTES_F32 = 69   # x, A, B are fp64 in the float flavour: read x8 r4 I4 A8 B8 C4 a4 t4 = 44, write x8 y4 I4 t4 rew4 done1 = 25
 
@@ -333,6 +333,10 @@ def run_b200(args):
     else:
         env = V.PHVec(n, dtype=torch.float32, seed=0, env_offset=rank * n)
     env.reset()
+    # stand-alone step kernels (HBM rows of SURVEY 8d), each timed alone -- before the long rollout loop, i.e. in the same
+    # burst state the HBM peak of MEASURED_PEAKS.json was measured in (the water-tank kernel is co-limited by its 40 MUFU.SQRT
+    # per env-step, so its time follows the SM clock)
+    aux = aux_step_rooflines(V, pk) if (rank == 0 and not args.no_aux and is_wt) else None
     bs = torch.empty((T, n, S), dtype=torch.float32, device="cuda")
     bo = torch.empty((T, n, 4), dtype=torch.float32, device="cuda")
     stats = torch.zeros(8, dtype=torch.float64, device="cuda")
@@ -436,8 +440,8 @@ def run_b200(args):
             line["sfu"] = {"achieved_gops": mufu / 1e9, "peak_gops": mufu_peak / 1e9, "frac": mufu / mufu_peak,
                            "note": "MUFU ops/s (hidden tanh + plant sqrt + Box-Muller) vs 148 SM x 16/clk at the median SM clock "
                                    "under load (tanh.approx microbenchmark on this pool: 16.3 per clk per SM)"}
-        if not args.no_aux and is_wt:
-            line["roofline_step"] = aux_step_rooflines(V, pk)
+        if aux is not None:
+            line["roofline_step"] = aux
         if not args.no_cpu_baseline and world == 1 and args.workload in ("wt", "ph"):
             line["cpu_baseline"] = cpu_baseline(w, args.cpu_seconds, sd)
         print(json.dumps(line), flush=True)
