@@ -32,7 +32,7 @@ def _agents(kind, S, H, n=2):
     return out
 
 
-def _data(agent, S, L=6000, seed=0):
+def _data(agent, S, L=40000, seed=0):
     g = torch.Generator(device="cuda").manual_seed(seed)
     state = torch.rand(L, S, device="cuda", generator=g) * 10
     state[:, -1] = torch.rand(L, device="cuda", generator=g) * 50 - 25           # an integrated error
@@ -73,8 +73,10 @@ def _grad_tc(f, data, idx, agent):
 
 
 @pytest.mark.parametrize("kind,S,H,B", [("modular", 4, 256, 300), ("modular", 3, 128, 1000), ("plain", 30, 256, 257), ("plain", 4, 128, 128),
-                                        ("modular", 4, 256, 4096)])
+                                        ("modular", 4, 256, 4096), ("modular", 4, 256, 20001), ("plain", 12, 128, 33000)])
 def test_tc_gradient_and_every_stage_match_autograd(kind, S, H, B):
+    # 20 001 / 33 000 rows: 157 / 258 row tiles -> every weight-gradient CTA walks over 5-9 row tiles (its hi / lo buffer pipeline
+    # wraps around several times) and the last row tile is ragged
     import pime_b200._lib as L
     import pime_b200.rl as R
     torch.backends.cuda.matmul.allow_tf32 = False
