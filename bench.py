@@ -352,12 +352,12 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)   # NVML initialisation takes a rank-dependent 10-100 ms: keep it out of the timed region
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     for _ in range(max(args.warmup, 0)):
         step()
     barrier()
-    sampler = ClockSampler(local)
     sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record()
     for i in range(args.steps):
         step()
