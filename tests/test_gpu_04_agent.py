@@ -177,6 +177,34 @@ def test_train_and_evaluate_smoke(tmp_path):
     assert all(np.isfinite(h.get("train/critic_loss", 0.0)) for h in hist)
 
 
+def test_train_and_evaluate_with_the_default_eval_env(tmp_path):
+    """Arguments.env_eval = None is the default (run.py:127: `env_eval = deepcopy(env)`): the PreprocessEnv wrapper and the
+    device env underneath must survive copy.deepcopy (advisor finding, round 1) and the copy must be independent."""
+    import pime_b200.rl as R
+    env = _make(WT, 16)
+    args = R.Arguments(if_on_policy=True)
+    args.agent = R.MODELS["residualppo"]()
+    args.env, args.env_eval = env, None
+    args.cwd = str(tmp_path / "run")
+    args.net_dim, args.batch_size, args.repeat_times, args.target_step = 32, 256, 1, 16 * 200
+    args.max_memo = args.target_step
+    args.break_step, args.eval_gap, args.eval_times1, args.eval_times2 = 2 * 16 * 200, 1, 8, 8
+    args.residual_kwargs = {"init_K": env.K.reshape(-1, 1)}
+    env.target_return = 1e9
+    R.configure_logger(0, None)
+    test_dirs = []
+    args.test_render = lambda agent, d: test_dirs.append(d)              # called at step 0 and every test_render_times steps
+    args.test_render_times = 16 * 200
+    agent, buf = R.train_and_evaluate(args)
+    assert buf.now_len == 16 * 200 and os.path.exists(os.path.join(args.cwd, "actor.pth"))
+    assert [os.path.basename(d) for d in test_dirs] == ["step_0", "step_3200", "step_6400"]
+    import copy
+    twin = copy.deepcopy(env)
+    assert twin.env.vec is not env.env.vec and torch.equal(twin.env.vec.h1, env.env.vec.h1)
+    twin.env.vec.h1.add_(1.0)
+    assert not torch.equal(twin.env.vec.h1, env.env.vec.h1)
+
+
 def test_cuda_graph_minibatch_step_is_transparent():
     """The recorded minibatch step (index draw + gather + forward + backward + Adam) leaves the training state untouched
     while it is being recorded, and trains like the eager step (same kernels, different index draws)."""
