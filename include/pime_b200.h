@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PIME_B200_ABI_VERSION 3
+#define PIME_B200_ABI_VERSION 4
 
 enum {
     PIME_OK = 0,
@@ -268,6 +268,9 @@ typedef struct pime_rollout_args {
     double *stats;                  /* device double[8], accumulated: sum(ret), sum(ret^2), n_episodes,
                                        sum|r-y_final|, sum(reward), n_steps, -, -; may be NULL               */
     int32_t *status;                /* device int32[1], set to PIME_E* on a device-side fault; may be NULL   */
+    int64_t ld;                     /* row length of the per-step buffers (eps, pnoise*, buf_*, env_action: element [t][i]
+                                       lives at t * ld + i); 0 = n.  ld > n lets a call work on a slice of a wider env
+                                       range whose buffers were allocated for the full range (pointers pre-offset)      */
 } pime_rollout_args;
 
 int pime_wt_rollout_f32(const pime_wt_config *cfg, int64_t n, const pime_wt_state *st, const pime_rollout_args *args, void *stream);
@@ -289,7 +292,11 @@ int pime_reduce_episode_stats_f64(int64_t n, const double *ep_return, double *st
 /* ---------------------------------------------------------------------------------------------------------
  * Host-buffer convenience entry (what an unmodified gym-style caller with numpy arrays uses): copies the
  * per-env state from pinned/pageable HOST arrays to the device scratch `st_dev`, runs the fused rollout and
- * copies ep_return[n] (and the final state) back.  All host<->device traffic is inside the call.
+ * copies ep_return[n] (and the final state) back.  All host<->device traffic is inside the call, which returns after
+ * the last byte has arrived.  Large env ranges (>= 8 waves of SM count x 256 envs, no stacking frames) are cut into up to 8 slices of whole waves and pipelined: the copy-in of slice k+1 and the copy-out
+ * of slice k-1 run on two internal streams under the rollout of slice k.  An env's random stream is keyed by its global
+ * id, so the result does not depend on the slicing; pime_set_host_slices(c) forces c slices of whole 256-env tiles
+ * (tests / tuning; 0 = automatic).
  * ------------------------------------------------------------------------------------------------------- */
 int pime_wt_rollout_host_f32(const pime_wt_config *cfg, int64_t n, const pime_wt_state *st_host, const pime_wt_state *st_dev,
                              const pime_rollout_args *args, float *ep_return_host, void *stream);
@@ -297,6 +304,7 @@ int pime_wt_rollout_host_f32(const pime_wt_config *cfg, int64_t n, const pime_wt
  * x, y, r, I of the final state are copied back.  `table` is the DEVICE table of pime_ph_table_build. */
 int pime_ph_rollout_host_f32(const pime_ph_config *cfg, const float *table, int64_t n, const pime_ph_state *st_host,
                              const pime_ph_state *st_dev, const pime_rollout_args *args, float *ep_return_host, void *stream);
+int pime_set_host_slices(int32_t slices);
 
 /* ---------------------------------------------------------------------------------------------------------
  * PPO learner: one minibatch step of AgentPPO.update_net (elegantrl/agent.py:635-658) on the GPU-resident replay

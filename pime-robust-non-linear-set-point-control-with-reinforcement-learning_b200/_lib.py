@@ -63,7 +63,7 @@ class RolloutArgs(C.Structure):
                 ("priorK_host", C.POINTER(C.c_double)), ("T", C.c_int32), ("auto_reset", C.c_int32),
                 ("reward_scale", C.c_double), ("gamma", C.c_double), ("seed", C.c_uint64), ("env_offset", C.c_uint64),
                 ("tick0", C.c_uint32), ("keep_params", C.c_uint32), ("eps", vp), ("pnoise1", vp), ("pnoise2", vp),
-                ("buf_state", vp), ("buf_other", vp), ("env_action", vp), ("stats", vp), ("status", vp)]
+                ("buf_state", vp), ("buf_other", vp), ("env_action", vp), ("stats", vp), ("status", vp), ("ld", C.c_int64)]
 
 
 class PpoArgs(C.Structure):
@@ -85,7 +85,7 @@ SYMBOLS = [
     "pime_gae_scan", "pime_reduce_episode_stats_f32", "pime_reduce_episode_stats_f64",
     "pime_ppo_theta_count", "pime_ppo_theta_layout", "pime_ppo_work_floats", "pime_ppo_transpose", "pime_ppo_step", "pime_ppo_apply_grad",
     "pime_ppo_tc_work_bytes", "pime_ppo_tc_layout", "pime_ppo_grad_tc", "pime_ppo_close_step",
-    "pime_wt_rollout_host_f32", "pime_ph_rollout_host_f32", "pime_abi_version", "pime_last_error", "pime_device_info", "pime_philox_probe",
+    "pime_wt_rollout_host_f32", "pime_ph_rollout_host_f32", "pime_set_host_slices", "pime_abi_version", "pime_last_error", "pime_device_info", "pime_philox_probe",
 ]
 
 _lib = None

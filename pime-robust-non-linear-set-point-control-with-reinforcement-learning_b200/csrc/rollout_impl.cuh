@@ -13,6 +13,7 @@ constexpr int kMaxS = 32;
 
 struct RolloutParams {
     int64_t n;
+    int64_t ld;             // row length of the per-step buffers (>= n)
     int T, deterministic, auto_reset, has_actor, keep_params;
     float a_std;            // exp(a_std_log)
     double reward_scale, gamma;
@@ -200,7 +201,7 @@ template <typename Plant> struct Stepper {
         const int S = rp.S;
         // ---- noise
         float eps = 0.0f, z0 = 0.0f, z1 = 0.0f;
-        const int64_t q = (int64_t)s * n + ii;
+        const int64_t q = (int64_t)s * rp.ld + ii;
         const bool need_eps = !rp.deterministic && rp.eps == nullptr;
         const bool need_pn = plant.uses_process_noise() && rp.pn1 == nullptr;
         if (need_eps || need_pn) {
@@ -502,7 +503,8 @@ inline int fill_rollout_params(const pime_rollout_args *a, int64_t n, int S, Rol
     PIME_REQUIRE((a->buf_state == nullptr) == (a->buf_other == nullptr), "buf_state/buf_other must both be given or both NULL");
     PIME_REQUIRE((a->pnoise1 == nullptr) == (a->pnoise2 == nullptr), "pnoise1/pnoise2 must both be given or both NULL");
     rp = RolloutParams{};
-    rp.n = n; rp.T = a->T; rp.deterministic = a->deterministic; rp.auto_reset = a->auto_reset;
+    PIME_REQUIRE(a->ld == 0 || a->ld >= n, "ld must be 0 or >= n");
+    rp.n = n; rp.ld = a->ld ? a->ld : n; rp.T = a->T; rp.deterministic = a->deterministic; rp.auto_reset = a->auto_reset;
     rp.has_actor = a->actor != nullptr;
     rp.keep_params = a->keep_params != 0;
     rp.a_std = expf(a->a_std_log);

@@ -1,30 +1,41 @@
 #include "rollout_wt.cuh"
+#include "host_pipe.cuh"
 using namespace pime;
 extern "C" int pime_wt_rollout_f32(const pime_wt_config *cfg, int64_t n, const pime_wt_state *st, const pime_rollout_args *args,
                                    void *stream) {
     return wt_rollout_impl<float>(cfg, n, st, args, stream);
 }
 
-// Host-buffer entry: H2D of the per-env state, fused rollout, D2H of ep_return (+ final state).
+// Host-buffer entry: H2D of the per-env state, fused rollout, D2H of ep_return (+ final state), pipelined over env slices
+// (host_pipe.cuh).  The stacking observation keeps its frames [3 num_stack][n] with stride n: one slice.
 extern "C" int pime_wt_rollout_host_f32(const pime_wt_config *cfg, int64_t n, const pime_wt_state *h, const pime_wt_state *d,
                                         const pime_rollout_args *args, float *ep_return_host, void *stream) {
     PIME_REQUIRE(cfg && h && d && args, "null pointer");
     PIME_REQUIRE(d->ep_return, "device ep_return scratch is required");
+    PIME_REQUIRE(n >= 0, "negative n");
     if (int rc = require_device()) return rc;
-    cudaStream_t s = (cudaStream_t)stream;
-    const size_t b = (size_t)n * sizeof(float);
-    void *const hs[7] = {h->h1, h->h2, h->r, h->I, h->a1, h->a2, h->Kp};
-    void *const ds[7] = {d->h1, d->h2, d->r, d->I, d->a1, d->a2, d->Kp};
-    for (int j = 0; j < 7; ++j)
-        if (hs[j] && ds[j]) PIME_CUDA(cudaMemcpyAsync(ds[j], hs[j], b, cudaMemcpyHostToDevice, s));
-    if (h->t) PIME_CUDA(cudaMemcpyAsync(d->t, h->t, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    if (h->episode) PIME_CUDA(cudaMemcpyAsync(d->episode, h->episode, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    PIME_CUDA(cudaMemsetAsync(d->ep_return, 0, b, s));
-    if (int rc = wt_rollout_impl<float>(cfg, n, d, args, stream)) return rc;
-    if (ep_return_host) PIME_CUDA(cudaMemcpyAsync(ep_return_host, d->ep_return, b, cudaMemcpyDeviceToHost, s));
-    for (int j = 0; j < 4; ++j)
-        if (hs[j] && ds[j]) PIME_CUDA(cudaMemcpyAsync(hs[j], ds[j], b, cudaMemcpyDeviceToHost, s));
-    PIME_CUDA(cudaStreamSynchronize(s));
+    const HostArr arr[9] = {{h->h1, d->h1, 4, true}, {h->h2, d->h2, 4, true}, {h->r, d->r, 4, true}, {h->I, d->I, 4, true},
+                            {h->a1, d->a1, 4, false}, {h->a2, d->a2, 4, false}, {h->Kp, d->Kp, 4, false},
+                            {h->t, d->t, 4, false}, {h->episode, d->episode, 4, false}};
+    const bool single = cfg->obs_mode == PIME_WT_OBS_STACKING;
+    auto launch = [&](int64_t off, int64_t cnt, const pime_rollout_args &a) {
+        pime_wt_state st = *d;
+        auto sh = [&](void *p, int elem) { return p ? (void *)((char *)p + off * elem) : nullptr; };
+        st.h1 = sh(d->h1, 4); st.h2 = sh(d->h2, 4); st.r = sh(d->r, 4); st.I = sh(d->I, 4);
+        st.a1 = sh(d->a1, 4); st.a2 = sh(d->a2, 4); st.Kp = sh(d->Kp, 4);
+        st.t = (int32_t *)sh(d->t, 4); st.episode = (uint32_t *)sh(d->episode, 4);
+        st.ep_return = sh(d->ep_return, 4); st.last_h1 = sh(d->last_h1, 4); st.last_h2 = sh(d->last_h2, 4);
+        pime_rollout_args b = a;
+        shift_step_buffers(b, off, cfg->obs_mode == PIME_WT_OBS_INTEGRATOR ? 4 : 3, 4);   // (stacking: one slice, off = 0)
+        return wt_rollout_impl<float>(cfg, cnt, &st, &b, stream);
+    };
+    return host_pipelined_rollout(n, arr, 9, (float *)d->ep_return, ep_return_host, args, (cudaStream_t)stream, launch, single);
+}
+
+// tests / tuning: force the number of env slices of the host-buffer entries (0 = automatic)
+extern "C" int pime_set_host_slices(int32_t slices) {
+    PIME_REQUIRE(slices >= 0 && slices <= kMaxSlices, "0 <= slices <= 8");
+    host_slices_override() = slices;
     return PIME_OK;
 }
 

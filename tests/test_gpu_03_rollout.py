@@ -425,3 +425,48 @@ def test_rollout_host_entries_equal_the_device_rollout(V):
     d.check_status()
     assert torch.equal(oc["buf_state"], od["buf_state"]) and torch.equal(oc["buf_other"], od["buf_other"])
     assert torch.equal(c.ep_return.cpu(), od["ep_return_host"]) and torch.equal(c.x.cpu(), hp["x"])
+
+
+@pytest.mark.parametrize("n,slices,T", [(1000, 3, 60), (5000, 8, 20), (2 * 4 * 148 * 256 + 777, 0, 4)])
+def test_sliced_host_entries_equal_the_device_rollout(V, n, slices, T):
+    """The host-buffer entries pipeline copy-in / rollout / copy-out over env slices (csrc/host_pipe.cuh; automatically from
+    8 waves of 148 x 256 envs on, forced here through pime_set_host_slices for the small cases): same bytes as one launch over
+    all envs -- replay rows, final state, episode returns and the accumulated statistics -- with stochastic actions and in-kernel resets."""
+    import pime_b200._lib as L
+    seed = 11
+    L.check(L.lib().pime_set_host_slices(slices))
+    try:
+        sd = _torch_default_params("modular", 64, 4, 1, seed=2)
+        pack = V.ActorPack("modular", 4, 64, 1).update(sd)
+        a = V.WaterTankVec(n, dtype=torch.float32, seed=seed, env_offset=5)
+        b = V.WaterTankVec(n, dtype=torch.float32, seed=seed, env_offset=5)
+        a.reset(); b.reset()
+        hostst = {k: getattr(b, k).cpu().pin_memory() for k in ("h1", "h2", "r", "I", "a1", "a2", "Kp", "t", "episode")}
+        for k in ("h1", "h2", "r", "I", "a1"):
+            getattr(b, k).zero_()
+        sa, sb = torch.zeros(8, dtype=torch.float64, device="cuda"), torch.zeros(8, dtype=torch.float64, device="cuda")
+        oa = a.rollout(T, -K_WT, actor=pack, stats=sa, auto_reset=True, replay=True)
+        ob = b.rollout_host(hostst, T, -K_WT, actor=pack, stats=sb, auto_reset=True, replay=True)
+        assert torch.equal(oa["buf_state"], ob["buf_state"]) and torch.equal(oa["buf_other"], ob["buf_other"])   # [T][n][.] rows, ld = n
+        for k in ("h1", "h2", "r", "I"):
+            assert torch.equal(getattr(a, k).cpu(), hostst[k]), k
+        assert torch.equal(a.ep_return.cpu(), ob["ep_return_host"]) and torch.equal(a.a1, b.a1) and torch.equal(a.episode, b.episode)
+        np.testing.assert_allclose(host(sa)[:6], host(sb)[:6], rtol=1e-12)          # atomics in a different order
+
+        sdp = _torch_default_params("modular", 32, 3, 1, seed=3)
+        packp = V.ActorPack("modular", 3, 32, 1).update(sdp)
+        c = V.PHVec(n, dtype=torch.float32, seed=seed)
+        d = V.PHVec(n, dtype=torch.float32, seed=seed)
+        c.reset(); d.reset()
+        hp = {k: getattr(d, k).cpu().pin_memory() for k in d.HOST_FIELDS}
+        for k in ("x", "y", "A", "B", "qc_V"):
+            getattr(d, k).zero_()
+        oc = c.rollout(T, -K_PH, actor=packp, replay=True)
+        od = d.rollout_host(hp, T, -K_PH, actor=packp, replay=True)
+        assert torch.equal(oc["buf_state"], od["buf_state"]) and torch.equal(oc["buf_other"], od["buf_other"])
+        d.check_status()
+        for k in ("x", "y", "r", "I"):
+            assert torch.equal(getattr(c, k).cpu(), hp[k]), k
+        assert torch.equal(c.ep_return.cpu(), od["ep_return_host"])
+    finally:
+        L.check(L.lib().pime_set_host_slices(0))
