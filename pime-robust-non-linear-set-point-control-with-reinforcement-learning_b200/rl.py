@@ -295,6 +295,7 @@ class FusedLearner:
             self._args = (key, a, C.byref(a), data)
         a = self._args[1]
         a.idx = idx.data_ptr()
+        self._hyper(a, agent)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         L.check(self._step_fn(self._args[2], stream))
         if grad_out is not None and grad_out is self.grad:   # data parallel: mean gradient over the job, then Adam
@@ -302,6 +303,14 @@ class FusedLearner:
             L.check(L.lib().pime_ppo_apply_grad(self._args[2], L.ptr(grad_out), C.c_float(1.0 / torch.distributed.get_world_size()),
                                                 stream))
         self.steps += 1
+
+    @staticmethod
+    def _hyper(a, agent):
+        """The scalars of the cached argument block follow the agent / optimizer (a learning-rate change between two
+        update_net calls must reach the kernels)."""
+        grp = agent.optimizer.param_groups[0]
+        a.ratio_clip, a.lambda_entropy = agent.ratio_clip, agent.lambda_entropy
+        a.lr, a.beta1, a.beta2, a.eps = grp["lr"], grp["betas"][0], grp["betas"][1], grp["eps"]
 
     def dist_grad(self):
         if self.grad is None:
@@ -331,6 +340,7 @@ class FusedLearner:
             self._args = (key, a, C.byref(a), data)
         a = self._args[1]
         a.idx = idx.data_ptr()
+        self._hyper(a, agent)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         lib = L.lib()
         L.check(lib.pime_ppo_grad_tc(self._args[2], L.ptr(self.work_tc), L.ptr(grad), stream))
