@@ -419,6 +419,38 @@ class ReplayBuffer:
         self.next_idx = self.now_len = 0
         self.if_full = False
 
+    def gather(self):
+        """Single-learner mode: every rank receives the whole job's on-policy replay.  The local buffer holds
+        time-major rows [T, n_rank, .] of this rank's contiguous env range (``shard_range``); the result is a time-major
+        buffer over ALL envs, [T, sum(n_rank), .], ranks in order -- the rows one process would have written had it owned
+        every env.  One all-gather (NCCL on GPUs) of the (S + 4)-float rows; ranks may own different numbers of envs (the
+        shorter ones are padded for the collective).  Without torch.distributed it returns self."""
+        if not _dist_on():
+            return self
+        dist = torch.distributed
+        self._flush()
+        world, n = dist.get_world_size(), self.num_envs
+        rows = self.max_len if self.if_full else self.next_idx
+        assert rows % n == 0, "the time-major buffer holds whole steps"
+        T = rows // n
+        meta = torch.tensor([n, T], dtype=torch.int64, device=self.device)
+        metas = [torch.empty_like(meta) for _ in range(world)]
+        dist.all_gather(metas, meta)
+        ns = [int(m[0]) for m in metas]
+        assert all(int(m[1]) == T for m in metas), "every rank must hold the same number of steps"
+        n_max, W = max(ns), self.state_dim + self.other_dim
+        mine = torch.zeros((T, n_max, W), dtype=torch.float32, device=self.device)
+        mine[:, :n, :self.state_dim] = self.buf_state[:rows].view(T, n, self.state_dim)
+        mine[:, :n, self.state_dim:] = self.buf_other[:rows].view(T, n, self.other_dim)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        full = torch.cat([p[:, :k] for p, k in zip(parts, ns)], dim=1)       # [T, sum(ns), S + 4]
+        out = ReplayBuffer(T * sum(ns), self.state_dim, 1, True, False, True, num_envs=sum(ns), device=str(self.device))
+        out.buf_state[:] = full[..., :self.state_dim].reshape(-1, self.state_dim)
+        out.buf_other[:] = full[..., self.state_dim:].reshape(-1, self.other_dim)
+        out.next_idx = out.now_len = T * sum(ns)
+        return out
+
     def sample_all(self):
         """(reward[L], mask[L], action[L,1], noise[L,1], state[L,S]) -- replay.py:353-368."""
         o = self.buf_other[:self.now_len]

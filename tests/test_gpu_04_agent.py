@@ -478,6 +478,14 @@ flat = torch.cat([p.detach().reshape(-1) for p in list(agent.act.parameters()) +
 ref = flat.clone(); dist.broadcast(ref, 0)
 assert torch.equal(flat, ref), "replicas diverged"
 assert torch.isfinite(flat).all()
+# single-learner mode: the NCCL all-gather of the sharded replay gives every rank the rows of all 2 n envs, time-major,
+# rank 0's env range first -- and one rollout over the whole range on one GPU writes exactly those rows
+full = buf.gather()
+assert full.num_envs == 2 * n and full.now_len == 2 * buf.now_len
+mine = full.buf_state.view(-1, 2 * n, env.state_dim)[:, rank * n:(rank + 1) * n]
+assert torch.equal(mine.reshape(-1, env.state_dim), buf.buf_state[:buf.now_len])
+chk = full.buf_other.double().sum(); ref2 = chk.clone(); dist.broadcast(ref2, 0)
+assert torch.equal(chk, ref2)
 if rank == 0: print("DIST_OK", agent.learner_path)
 dist.destroy_process_group()
 """

@@ -189,6 +189,50 @@ def _ddp_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = R.shard_range(5, rank, world)                           # 5 envs over 2 ranks: 3 + 2 (uneven on purpose)
+    n, T, S = hi - lo, 4, 3
+    buf = R.ReplayBuffer(T * n, S, 1, True, False, True, num_envs=n, device="cpu")
+    bs, bo = buf.rollout_views(T)
+    t = torch.arange(T, dtype=torch.float32).view(T, 1, 1)
+    e = torch.arange(lo, hi, dtype=torch.float32).view(1, n, 1)
+    bs.copy_((100 * t + e).expand(T, n, S) + torch.arange(S, dtype=torch.float32) * 0.1)      # row (t, global env) is recognisable
+    bo.copy_((1000 + 100 * t + e).expand(T, n, 4))
+    buf.commit_rollout(T)
+    full = buf.gather()
+    q.put((rank, full.num_envs, full.now_len, full.buf_state.clone().numpy(), full.buf_other.clone().numpy()))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_replay_gather_is_time_major_over_all_envs():
+    """ReplayBuffer.gather (single-learner mode): both ranks end up with the [T, 5, .] rows one process owning all five envs
+    would hold, although the ranks own 3 and 2 envs."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda t: t[0])
+    [p.join(timeout=60) for p in ps]
+    T, N, S = 4, 5, 3
+    t = np.arange(T, dtype=np.float32).reshape(T, 1, 1)
+    e = np.arange(N, dtype=np.float32).reshape(1, N, 1)
+    want_s = (np.broadcast_to(100 * t + e, (T, N, S)) + np.arange(S, dtype=np.float32) * 0.1).reshape(T * N, S).astype(np.float32)
+    want_o = np.broadcast_to(1000 + 100 * t + e, (T, N, 4)).reshape(T * N, 4).astype(np.float32)
+    for rank, n_envs, now_len, bs, bo in res:
+        assert n_envs == N and now_len == T * N
+        assert np.array_equal(bs, want_s) and np.array_equal(bo, want_o)
+
+
+def test_replay_gather_without_a_process_group_is_the_buffer_itself():
+    buf = R.ReplayBuffer(8, 3, 1, True, False, True, num_envs=2, device="cpu")
+    assert buf.gather() is buf
+
+
 def test_world_size_2_grad_allreduce_and_global_advantage_moments():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
