@@ -177,6 +177,49 @@ def test_full_size_properties_at_2_pow_20_envs():
     assert -4000 < mean_ret < -500                                          # the P prior on random set-points (SquareDistance)
 
 
+def test_full_size_properties_at_2_pow_23_ph_envs():
+    """BASELINE configs[3] at its full size (2^23 pH envs, T = 50, Modular-128): zero-initialised actor == prior-only policy
+    bit for bit (x is fp64 in both), any split of the ensemble-member range reproduces the unsplit sweep, every env is done
+    exactly at the TimeLimit and restarted by the in-kernel reset, no table fault, pH inside the table's range."""
+    import pime_b200.vec as V
+    n, T = 1 << 23, 50
+    K = np.array([-0.02, 0.02, 0.035])                                     # PH1D...Integrator K (ph.py), priorK = -K
+    H = 128
+    sd = {}
+    rng = np.random.default_rng(1)
+    for name, o, i in [("other_net.0", H, 2), ("other_net.2", H // 2, H), ("integrator_net.0", H, 1),
+                       ("integrator_net.2", H // 2, H), ("net.0", H, H), ("net.2", 1, H)]:
+        b = 1.0 / np.sqrt(i)
+        sd[name + ".weight"] = rng.uniform(-b, b, (o, i)).astype(np.float32)
+        sd[name + ".bias"] = rng.uniform(-b, b, o).astype(np.float32)
+    sd["net.2.weight"][:] = 0.0
+    sd["net.2.bias"][:] = 0.0
+    actor = V.ActorPack("modular", 3, H, 1).update(sd)
+
+    def run(n_, off, use_actor):
+        env = V.PHVec(n_, dtype=torch.float32, seed=3, env_offset=off)
+        env.reset()
+        stats = torch.zeros(8, dtype=torch.float64, device="cuda")
+        env.rollout(T + 2, -K, actor=actor if use_actor else None, deterministic=True, auto_reset=True, stats=stats)
+        env.check_status()
+        return env, stats.cpu().numpy()
+
+    whole, st = run(n, 0, True)
+    prior, st_p = run(n, 0, False)
+    assert torch.equal(whole.x, prior.x) and torch.equal(whole.y, prior.y) and torch.equal(whole.ep_return, prior.ep_return)
+    np.testing.assert_allclose(st[:6], st_p[:6], rtol=1e-12)
+    assert st[2] == n and st[5] == n * (T + 2) and int(whole.t.min()) == 2 == int(whole.t.max())
+    assert int(whole.episode.min()) == 2
+    assert 0.0 < float(whole.y.min()) and float(whole.y.max()) < 11.8         # pH[0] = 11.70 is the table's largest entry (KAT-3)
+    keep = {k: getattr(whole, k).clone() for k in ("x", "y", "I", "ep_return", "qww_V")}
+    del whole, prior
+    torch.cuda.empty_cache()
+    lo, _ = run(n // 2, 0, True)
+    hi, _ = run(n // 2, n // 2, True)
+    for k, v in keep.items():
+        assert torch.equal(torch.cat([getattr(lo, k), getattr(hi, k)]), v), k
+
+
 def test_reset_from_last_state_follows_the_reference_script(G, golden):
     """reset_from_last_state=True (nonlinear_watertank.py:904-910, :819-821; ph.py:417-420, :345-346) against the
     scripted run of the reference in tests/golden/last_state.npz (oracle/gen_golden.py:gen_last_state): the ensemble
