@@ -32,3 +32,9 @@ extern "C" int pime_ph_rollout_host_f32(const pime_ph_config *cfg, const float *
     };
     return host_pipelined_rollout(n, arr, 11, (float *)d->ep_return, ep_return_host, args, (cudaStream_t)stream, launch, false);
 }
+
+#ifdef PIME_PROFILE_WORKER
+extern "C" int pime_debug_worker_prof_ph(double *out16) {
+    return cudaMemcpyFromSymbol(out16, pime::tc::g_worker_prof, 16 * sizeof(double)) == cudaSuccess ? 0 : -3;
+}
+#endif
