@@ -801,7 +801,11 @@ int pime_ppo_close_step(const pime_ppo_args *a, void *stream) {
     return PIME_OK;
 }
 
-int pime_ppo_grad_tc(const pime_ppo_args *a, void *work_tc, float *grad, void *stream) {
+}  // extern "C"
+
+// parts: bit 0 = everything but the actor's weight gradients (after it the critic's part of grad, the bias gradients of both
+// nets and d a_std_log are complete), bit 1 = the actor's weight gradients (needs bit 0 of the same step to have run).
+static int ppo_grad_tc_impl(const pime_ppo_args *a, void *work_tc, float *grad, void *stream, int parts) {
     using namespace tcl;
     PIME_REQUIRE(a && a->actor && work_tc && grad, "null ppo args / work / grad");
     PIME_REQUIRE(a->theta && a->state && a->loss_ring && a->ring_len >= 2, "null theta / state / loss ring");
@@ -830,6 +834,9 @@ int pime_ppo_grad_tc(const pime_ppo_args *a, void *work_tc, float *grad, void *s
     c.dz_scale[1] = pow2B * 16.0f;    // critic: |d out| B <= 1 / (std(r_sum) + 1e-5)
     const float un_a = 1.0f / c.dz_scale[0], un_c = 1.0f / c.dz_scale[1];
 
+    const Net &A = pl.act, &C = pl.cri;
+    const int actA = ACT_TANH, actC = ACT_RELU;
+    if (parts & 1) {
     PIME_CUDA(cudaMemsetAsync(grad, 0, (size_t)pl.n_theta * sizeof(float), s));
     split_weights_kernel<<<dim3(64, pl.ws.n), 256, 0, s>>>(pl.ws, th, w);
     PIME_LAUNCH_CHECK();
@@ -838,8 +845,6 @@ int pime_ppo_grad_tc(const pime_ppo_args *a, void *work_tc, float *grad, void *s
     rstd_kernel<<<1, 1024, 0, s>>>(c);
     PIME_LAUNCH_CHECK();
 
-    const Net &A = pl.act, &C = pl.cri;
-    const int actA = ACT_TANH, actC = ACT_RELU;
     auto B_ = [&](const Net &d, int j) { return th + d.theta_off + d.src[j]; };
     auto run_gemm = [&](GemmBatch &gb) {
         gb.row_tiles = RT;
@@ -909,13 +914,19 @@ int pime_ppo_grad_tc(const pime_ppo_args *a, void *work_tc, float *grad, void *s
         g.p[g.n++] = bwd(w, pl, un_c, pl.Z[6], 0, HC, pl.WT[6], HC, H, actC, pl.A[5], pl.Z[5], nullptr);
         if (int rc = run_gemm(g)) return rc;
     }
-    // ---- weight gradients
-    {
+    }   // parts & 1 (the critic's weight gradients below belong to it too)
+    // ---- weight gradients: all matrices in one launch, or the critic's (bit 0) and the actor's (bit 1) in separate launches
+    // so that a data-parallel caller can all-reduce the critic's part while the actor's is still being computed
+    for (int part = 1; part <= 2; part <<= 1) {
+        if (!(parts & part)) continue;
+        if (parts == 3 && part == 2) break;                 // one launch did both
+        const bool do_act = parts == 3 || part == 2, do_cri = parts == 3 || part == 1;
         WgBatch g{};
         g.grad = grad; g.row_tiles = RT;
         auto W_ = [&](const Net &d, int j) { return d.theta_off + d.src[j]; };
         const int S = c.S;
-        if (mod) {
+        if (!do_act) {
+        } else if (mod) {
             g.p[g.n++] = wg(w, pl, un_a, pl.Z[0], 0, H, pl.X, 1, 64, W_(A, 0), A.So, 0, A.So, kBiasCol, W_(A, 1));                 // other_net.0
             g.p[g.n++] = wg(w, pl, un_a, pl.Z[1], 0, H, pl.X, 1, 64, W_(A, 4), S - A.So, A.So, S, kBiasCol, W_(A, 5));            // integrator_net.0
             g.p[g.n++] = wg(w, pl, un_a, pl.Z[2], 0, Hh, pl.A[0], HC, H, W_(A, 2), H, 0, H, -1, 0);                               // other_net.2
@@ -926,15 +937,28 @@ int pime_ppo_grad_tc(const pime_ppo_args *a, void *work_tc, float *grad, void *s
             g.p[g.n++] = wg(w, pl, un_a, pl.Z[2], 0, H, pl.A[0], HC, H, W_(A, 2), H, 0, H, -1, 0);
             g.p[g.n++] = wg(w, pl, un_a, pl.Z[4], 0, H, pl.A[2], HC, H, W_(A, 4), H, 0, H, -1, 0);
         }
-        g.p[g.n++] = wg(w, pl, un_c, pl.Z[5], 0, H, pl.X, 1, 64, W_(C, 0), S, 0, S, kBiasCol, W_(C, 1));
-        g.p[g.n++] = wg(w, pl, un_c, pl.Z[6], 0, H, pl.A[5], HC, H, W_(C, 2), H, 0, H, -1, 0);
-        g.p[g.n++] = wg(w, pl, un_c, pl.Z[7], 0, H, pl.A[6], HC, H, W_(C, 4), H, 0, H, -1, 0);
+        if (do_cri) {
+            g.p[g.n++] = wg(w, pl, un_c, pl.Z[5], 0, H, pl.X, 1, 64, W_(C, 0), S, 0, S, kBiasCol, W_(C, 1));
+            g.p[g.n++] = wg(w, pl, un_c, pl.Z[6], 0, H, pl.A[5], HC, H, W_(C, 2), H, 0, H, -1, 0);
+            g.p[g.n++] = wg(w, pl, un_c, pl.Z[7], 0, H, pl.A[6], HC, H, W_(C, 4), H, 0, H, -1, 0);
+        }
         int mx = 1;
         for (int i = 0; i < g.n; ++i) mx = g.p[i].m_tiles * g.p[i].n_tiles > mx ? g.p[i].m_tiles * g.p[i].n_tiles : mx;
         int split = RT < 32 ? RT : 32;
         if (int rc = launch_batch(wgrad_mn_kernel, g, dim3(mx, split, g.n), kWgThreads, kWgSmem, s)) return rc;
     }
     return PIME_OK;
+}
+
+extern "C" {
+
+int pime_ppo_grad_tc(const pime_ppo_args *a, void *work_tc, float *grad, void *stream) {
+    return ppo_grad_tc_impl(a, work_tc, grad, stream, 3);
+}
+
+int pime_ppo_grad_tc_parts(const pime_ppo_args *a, void *work_tc, float *grad, int32_t parts, void *stream) {
+    PIME_REQUIRE(parts == 1 || parts == 2 || parts == 3, "parts must be 1, 2 or 3");
+    return ppo_grad_tc_impl(a, work_tc, grad, stream, parts);
 }
 
 }  // extern "C"

@@ -462,7 +462,7 @@ rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
 import pime_b200.gym_api as G, pime_b200.rl as R
-n, H = 64, 64
+n, H = 64, 128
 env = R.PreprocessEnv(G.make("NonLinearWaterTankChangingParamUniformGoalIntegrator-SquareDistance-v2", num_envs=n, dtype=torch.float32))
 env.env.vec.env_offset = rank * n
 torch.manual_seed(0)
@@ -474,6 +474,11 @@ for it in range(2):
     steps = agent.explore_env(env, buf, n * 200, 1.0, 0.99)
     agent.update_net(buf, steps, 256, 2)
 assert "all-reduce" in agent.learner_path, agent.learner_path
+# large minibatches: the tensor-core step, its critic-half all-reduce overlapped with the actor's weight-gradient launch
+agent.update_net(buf, steps, 2048, 2)
+assert "pime_ppo_grad_tc" in agent.learner_path and "all-reduce" in agent.learner_path, agent.learner_path
+agent.tc_allreduce_overlap = True                  # the two-part gradient call with the critic's half reduced on a side stream
+agent.update_net(buf, steps, 2048, 2)
 flat = torch.cat([p.detach().reshape(-1) for p in list(agent.act.parameters()) + list(agent.cri.parameters())])
 ref = flat.clone(); dist.broadcast(ref, 0)
 assert torch.equal(flat, ref), "replicas diverged"

@@ -160,6 +160,35 @@ def test_tc_steps_track_the_autograd_path(kind, S, H, B):
         assert float(d.max()) <= 0.6 * lr and float(d.mean()) <= 0.02 * lr, n1
 
 
+def test_tc_gradient_in_two_parts_equals_the_single_call():
+    """pime_ppo_grad_tc_parts: parts = 1 leaves the critic's half of the flat gradient (+ d a_std_log) final -- the all-reduce
+    of that half overlaps the actor's weight-gradient launch in a data-parallel job --, parts = 2 completes the actor's half."""
+    import pime_b200._lib as L
+    import pime_b200.rl as R
+    (agent,) = _agents("modular", 4, 256, 1)
+    data = _data(agent, 4)
+    idx = torch.randint(data[0].shape[0], size=(5000,), device="cuda")
+    f = R.FusedLearner(agent.act, agent.cri, 4, 256, agent.device)
+    f.load(agent.act, agent.cri)
+    whole, _ = _grad_tc(f, data, idx, agent)
+    whole = whole.clone()
+    f.step_tc(data, idx, agent)                              # builds the cached argument block; its Adam step is irrelevant here
+    f.load(agent.act, agent.cri)
+    args, stream = f._args[2], L.stream_ptr()
+    grad = torch.full_like(f.theta, 7.0)
+    L.check(L.lib().pime_ppo_grad_tc_parts(args, L.ptr(f.work_tc), L.ptr(grad), C.c_int32(1), stream))
+    torch.cuda.synchronize()
+    half = grad.clone()
+    scale = float(whole.abs().max())
+    assert float((half[f.cri_off:] - whole[f.cri_off:]).abs().max()) <= 1e-6 * scale      # critic + a_std_log: final (atomics reorder only)
+    ws = [o for t, o in f._slices(agent.act, agent.cri) if t.dim() == 2 and t.shape[0] > 1 and o < f.cri_off]   # (net.2 [1, H] comes from out_obj)
+    assert all(float(half[o:o + 8].abs().max()) == 0.0 for o in ws)                       # the actor's weight matrices are still zero
+    L.check(L.lib().pime_ppo_grad_tc_parts(args, L.ptr(f.work_tc), L.ptr(grad), C.c_int32(2), stream))
+    torch.cuda.synchronize()
+    assert float((grad - whole).abs().max()) <= 1e-6 * scale
+    assert torch.equal(grad[f.cri_off:], half[f.cri_off:])                                # part 2 does not touch the critic's half
+
+
 def test_update_net_takes_the_tensor_core_path_for_large_batches():
     import pime_b200.gym_api as G
     import pime_b200.rl as R
