@@ -298,7 +298,7 @@ def ph_e2e(env, actor, T, K, bs, bo, stats, steps, world, barrier, dist):
 
     e = time_e2e(step, steps, world, n * T, barrier, dist)
     e.update({"h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-              "api": "PHVec.rollout_host -> pime_ph_rollout_host_f32 (pinned host state in, ep_return + final state out)"})
+              "api": "PHVec.rollout_host -> pime_ph_rollout_host_f32 (pinned host state in, ep_return + final state out; copy-in / rollout / copy-out pipelined over env slices)"})
     return e
 
 
@@ -394,7 +394,7 @@ def run_b200(args):
 
         e2e = time_e2e(e2e_step, args.steps, world, n * T, barrier, dist)
         e2e.update({"h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "WaterTankVec.rollout_host -> pime_wt_rollout_host_f32 (pinned host state in, ep_return + final state out)"})
+                    "api": "WaterTankVec.rollout_host -> pime_wt_rollout_host_f32 (pinned host state in, ep_return + final state out; copy-in / rollout / copy-out pipelined over env slices)"})
     elif args.workload == "ph":
         e2e = ph_e2e(env, actor, T, K, bs, bo, stats, args.steps, world, barrier, dist)
 
