@@ -32,7 +32,9 @@
 //                       (w, b) pairs in registers);  other_net.0 -> Db as soon as the previous pass has released Db;
 //                       P1 integrator_net.2 -> Da[0:H/2];  E2 tanh(Db);  P2 other_net.2 -> Da[H/2:H];  E3 tanh(cat'),
 //                       cat' = Da = [integrator | other] (net.0's input columns are rotated in the pack);  P3 net.0 -> Db;
-//                       E4 tanh(Db) . net.2 during the NEXT pass's E1.
+//                       E4 tanh(Db) . net.2 during the NEXT pass's E1.  For H >= 128 the A operands of other_net.2 and
+//                       net.0 never touch shared memory: E2 / E3 write them as fp16 pairs IN PLACE over accumulator columns
+//                       they have already read and the MMAs take A from tensor memory (Geo::kTS, epilogue_ts, layer_ts).
 //   plain (:6-66) / CriticAdv (net.py:274-277): P0 net.0 -> X, P1 net.2 -> Y, P2 net.4 -> X, net.6 in the epilogue of X,
 //                       with (X, Y) = (Da, Db) on even passes and (Db, Da) on odd ones, so that P0 never waits.
 #pragma once
@@ -227,6 +229,18 @@ inline MlpParams make_mlp_params(const PackLayout &L, const void *pack) {
 template <int KIND, int H> struct Geo {
     static constexpr bool kModular = KIND == PIME_ACTOR_MODULAR;
     static constexpr bool kRelu = KIND == PIME_CRITIC_ADV;
+#ifndef PIME_NO_TMEM_A
+    // Modular actor, H >= 128: the A operands of other_net.2 and net.0 live in TENSOR memory.  Their epilogues read 64
+    // fp32 accumulator columns at a time with the 16-lane shapes (a warp owns 16 rows and ALL their columns, so writing the
+    // fp16 result IN PLACE over the first half of the columns it has already read is a purely warp-local hazard), pack pairs
+    // and tcgen05.st them back; the MMAs of those layers take A from TMEM.  That removes two thirds of the A-operand
+    // st.shared traffic and of the tcgen05 A fetch from the shared-memory pipe.  Measured against the shared-memory build
+    // (-DPIME_NO_TMEM_A) on one box, alternating: +6.9 % at H = 128 (pH sweep, 6.04e9 -> 6.46e9 env-steps/s), +4.2 % for the
+    // water tank at H = 128, +1.7 % at H = 256 (profiles/r02_tmem_a_operand.md).
+    static constexpr bool kTS = kModular && H >= 128;
+#else
+    static constexpr bool kTS = false;
+#endif
     static constexpr int NP = H / 32;                        // 32-column pieces per layer: one epilogue step (16 columns per
                                                              // worker half) and the granularity of the MMA pipelining
     static constexpr int ChunkArrivals = 2 * kRows;          // both halves write 16 columns of every piece
@@ -411,6 +425,41 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) 
         : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 16 lanes x 64 consecutive fp32 columns per warp (8 repetitions of the 16x256b atom): thread t gets, for x = 0..7,
+// v[4x], v[4x+1] = row t/4, columns 8x + 2(t%4), +1 and v[4x+2], v[4x+3] = row t/4 + 8, same columns -- the accumulator
+// fragment of the classic m16n8 MMA.  taddr's lane field is the first of the 16 lanes (a multiple of 16 inside the warp's
+// 32-lane quarter).
+__device__ __forceinline__ void tmem_ld_16x256b_x8_issue(uint32_t taddr, float (&v)[32]) {
+    uint32_t *u = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+          "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+          "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+          "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr)
+        : "memory");
+}
+// 16 lanes x 32 consecutive 32-bit columns per warp (8 repetitions of the 16x128b atom): thread t supplies, for x = 0..7,
+// p[2x] = row t/4, column 4x + t%4 and p[2x+1] = row t/4 + 8, same column -- exactly where the fp16 pairs packed from the
+// 16x256b fragment above belong when 64 fp32 columns become 32 columns of an fp16 A operand.
+__device__ __forceinline__ void tmem_st_16x128b_x8(uint32_t taddr, const uint32_t (&p)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr), "r"(p[0]), "r"(p[1]), "r"(p[2]),
+        "r"(p[3]), "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7]), "r"(p[8]), "r"(p[9]), "r"(p[10]), "r"(p[11]), "r"(p[12]), "r"(p[13]),
+        "r"(p[14]), "r"(p[15])
+        : "memory");
+}
+// A operand from tensor memory (M = 128 rows = lanes, K = 16 fp16 = 8 columns of fp16 pairs), B from shared memory
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+                 "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
 #ifdef PIME_PROFILE_WORKER
 __device__ double g_worker_prof[16];   // clocks of worker thread 0 of CTA 0 per segment of the modular pass (debug builds only)
 #define PIME_WTICK(k) { const long long c1_ = clock64(); wprof[k] += c1_ - c0_; c0_ = c1_; }
@@ -421,7 +470,7 @@ template <int KIND, int H> struct Engine {
     using G = Geo<KIND, H>;
     uint8_t *sA, *sRing;
     const Blk *tbl;
-    uint64_t *full, *empty, *a_rdy, *o_rdy, *d_ready, *out_rdy, *h_rdy, *l1b_rdy, *p0_rdy;
+    uint64_t *full, *empty, *a_rdy, *o_rdy, *d_ready, *out_rdy, *h_rdy, *l1b_rdy, *p0_rdy, *ts_rdy;
     float *sOutW, *sPart, *sL1i, *sI;
     uint32_t *tmem_slot;
     uint32_t tmem_base;
@@ -443,7 +492,8 @@ template <int KIND, int H> struct Engine {
         h_rdy = out_rdy + 1;
         l1b_rdy = h_rdy + 1;
         p0_rdy = l1b_rdy + 1;
-        tmem_slot = reinterpret_cast<uint32_t *>(p0_rdy + 1);
+        ts_rdy = p0_rdy + 1;              // [2][kMaxChunks]: 64-column slabs of the two in-TMEM A operands (kTS)
+        tmem_slot = reinterpret_cast<uint32_t *>(ts_rdy + 2 * kMaxChunks);
         sOutW = reinterpret_cast<float *>(smem + G::OutWOff);
         sPart = reinterpret_cast<float *>(smem + G::PartOff);
         sL1i = reinterpret_cast<float *>(smem + G::L1iOff);
@@ -451,7 +501,7 @@ template <int KIND, int H> struct Engine {
         const int tid = threadIdx.x;
         if (tid == 0) {
             for (int s = 0; s < G::Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-            for (int j = 0; j < 2 * kMaxChunks; ++j) mbar_init(&a_rdy[j], G::ChunkArrivals);
+            for (int j = 0; j < 2 * kMaxChunks; ++j) { mbar_init(&a_rdy[j], G::ChunkArrivals); mbar_init(&ts_rdy[j], G::ChunkArrivals); }
             mbar_init(&o_rdy[0], kOwnerThreads);
             mbar_init(&o_rdy[1], kOwnerThreads);
             mbar_init(d_ready, 1);
@@ -531,6 +581,44 @@ template <int KIND, int H> struct Engine {
         if (++m_st == (uint32_t)G::Stages) { m_st = 0; m_ph ^= 1; }
     }
 
+    // same, with the A operand in tensor memory: K = 16 slice kk of the operand = 8 columns of fp16 pairs at a_col + 8 kk
+    template <int N>
+    __device__ __forceinline__ void blk_ts(uint32_t a_col, int k16s, uint32_t d_col, uint64_t *x1 = nullptr) {
+        mbar_wait(&full[m_st], m_ph);
+        tc_fence_after();
+        if (elect_one()) {
+            const uint32_t b_addr = smem_u32(sRing) + m_st * kMaxBlkBytes;
+            constexpr uint32_t idesc = make_idesc(kRows, N);
+#pragma unroll 4
+            for (int kk = 0; kk < k16s; ++kk) {
+                const uint64_t bdesc = make_desc(b_addr + (uint32_t)kk * 2u * (N * 16), N * 16, 128);
+                mma_f16_ts(tmem_base + d_col, tmem_base + a_col + (uint32_t)kk * 8u, bdesc, idesc, 1u);
+            }
+            mma_commit(&empty[m_st]);
+            if (x1) mma_commit(x1);
+        }
+        __syncwarp();
+        if (++m_st == (uint32_t)G::Stages) { m_st = 0; m_ph ^= 1; }
+    }
+    // hidden layer whose A operand the feeding epilogue leaves in tensor memory at columns [a_col, a_col + H/2): the bias
+    // block (against the shared-memory ones operand), then the weight blocks, each as soon as the 64-column slabs it reads
+    // are stored (rdy[slab], parity par)
+    template <int N>
+    __device__ __forceinline__ void layer_ts(uint32_t d_col, uint32_t a_col, uint64_t *rdy, uint32_t par, uint64_t *e1) {
+        constexpr int K16 = H / 16, kpb = blk_k16(N, K16);
+        blk<N, true>((uint32_t)G::OnesOff, 1, d_col);
+        int waited = 0;
+#pragma unroll
+        for (int k = 0; k < K16; k += kpb) {
+            const int upto = ((k + kpb) * 16 + 63) / 64;
+            if (waited < upto) {
+                for (; waited < upto; ++waited) mbar_wait(&rdy[waited], par);
+                tc_fence_after();
+            }
+            blk_ts<N>(a_col + (uint32_t)k * 8u, kpb, d_col, k + kpb >= K16 ? e1 : nullptr);
+        }
+    }
+
     // K slices [K_LO, K_HI) of one hidden layer: (bias block first when BIAS, after waiting for the first `lag`
     // pieces when the accumulator aliases columns the feeding epilogue is still reading), then the weight blocks, each
     // as soon as the A pieces it reads are written.  abuf: which A tile the feeding epilogue writes.  e1/e2: barriers
@@ -579,12 +667,21 @@ template <int KIND, int H> struct Engine {
                 blk<H, true>(obs, 1, Db, l1b_rdy);
                 // P1: integrator_net.2 -> Da[0:H/2], once that epilogue has written its rows (all chunks arrive together).
                 // Da is free: the third epilogue of the previous pass was consumed piece by piece by its net.0 MMAs.
-                layer<Hh>(Da, (ep >> 1) & 1u, ep & 1u, 0, h_rdy, nullptr);
-                ++ep;
-                layer<Hh>(Da + Hh, (ep >> 1) & 1u, ep & 1u, 0, d_ready, nullptr);   // P2: other_net.2 -> Da[H/2:H], behind the epilogue of Db
-                ++ep;
-                layer<H>(Db, (ep >> 1) & 1u, ep & 1u, 0, d_ready, nullptr);         // P3: net.0 on cat' -> Db; net.2 is the workers' dot product
-                ++ep;
+                if constexpr (G::kTS) {
+                    // only the CUDA-core epilogue of integrator_net.0 uses a shared-memory A tile: tiles / barrier sets alternate per pass
+                    layer<Hh>(Da, ((uint32_t)q >> 1) & 1u, (uint32_t)q & 1u, 0, h_rdy, nullptr);
+                    // P2: other_net.2, A = tanh(Db) written IN PLACE over Db's first H/2 columns -> Da[H/2:H]
+                    layer_ts<Hh>(Da + Hh, Db, ts_rdy, (uint32_t)q & 1u, d_ready);
+                    // P3: net.0, A = tanh(cat') in place over Da's first H/2 columns -> Db (A of P2 is consumed: MMAs run in issue order)
+                    layer_ts<H>(Db, Da, ts_rdy + kMaxChunks, (uint32_t)q & 1u, d_ready);
+                } else {
+                    layer<Hh>(Da, (ep >> 1) & 1u, ep & 1u, 0, h_rdy, nullptr);
+                    ++ep;
+                    layer<Hh>(Da + Hh, (ep >> 1) & 1u, ep & 1u, 0, d_ready, nullptr);   // P2: other_net.2 -> Da[H/2:H], behind the epilogue of Db
+                    ++ep;
+                    layer<H>(Db, (ep >> 1) & 1u, ep & 1u, 0, d_ready, nullptr);         // P3: net.0 on cat' -> Db; net.2 is the workers' dot product
+                    ++ep;
+                }
             } else {
                 const uint32_t X = (q & 1) ? Db : Da, Y = (q & 1) ? Da : Db;   // Y = the previous pass's X
                 mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);
@@ -647,6 +744,37 @@ template <int KIND, int H> struct Engine {
             }
         }
     }
+    // kTS: A[:, 64 s .. 64 s + 64) = act(D[:, dcol + 64 s ..]) for the slabs s in [SB, SE), written as fp16 pairs IN PLACE over
+    // columns [dcol + 32 s, +32) of the same accumulator.  A warp owns 16 rows (lanes 32 (warp % 4) + 16 (warp / 4) ..) and all
+    // their columns, so the overwritten columns (they belong to slab s / 2 <= s) were read -- and waited for -- by this very
+    // warp.  One barrier arrive per slab; the MMAs of the next layer follow one slab behind.
+    template <int SB, int SE>
+    __device__ __forceinline__ void epilogue_ts(int warp, uint32_t dcol, uint64_t *rdy) {
+        if constexpr (SB < SE) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3) + 16 * (warp >> 2)) << 16) + dcol;
+            float v[2][32];
+            tmem_ld_16x256b_x8_issue(taddr + SB * 64, v[0]);
+#pragma unroll
+            for (int s = SB; s < SE; ++s) {
+                const int cur = (s - SB) & 1;
+                tmem_wait_ld();
+                if (s + 1 < SE) tmem_ld_16x256b_x8_issue(taddr + (s + 1) * 64, v[cur ^ 1]);   // columns beyond everything stored so far
+                uint32_t p[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) p[e] = pack_h2(act_pinned<G::kRelu>(v[cur][2 * e]), act_pinned<G::kRelu>(v[cur][2 * e + 1]));
+                if (s > SB) {   // the stores of the previous slab completed under this slab's MUFU work: signal them now
+                    tmem_wait_st();
+                    tc_fence_before();
+                    mbar_arrive(&rdy[s - 1]);
+                }
+                tmem_st_16x128b_x8(taddr + s * 32, p);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(&rdy[SE - 1]);
+        }
+    }
+
     // modular: tanh(integrator_net.0) straight from the fp32 integrated error (one input: w * I + b on the FMA pipe);
     // needs neither TMEM nor the tensor pipe, so it runs while the previous pass's net.0 is still accumulating.  Here a
     // thread owns ONE 8-column chunk (its 8 (w, b) pairs stay in registers for the call) and walks down the rows, RL rows
@@ -735,9 +863,10 @@ template <int KIND, int H> struct Engine {
 #endif
             for (int q = 0; q < passes; ++q) {
                 const int g = q & 1;
+                const uint32_t e1buf = G::kTS ? ((uint32_t)q & 1u) : (ep & 1u);   // kTS: only this epilogue uses a shared-memory tile
                 mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);              // the owners have written this pass's observation
                 PIME_WTICK(0)
-                epilogue_l1i<0>(tid, g, ep & 1u);                           // tanh(integrator_net.0) (net_residual.py:154), upper rows
+                epilogue_l1i<0>(tid, g, e1buf);                             // tanh(integrator_net.0) (net_residual.py:154), upper rows
                 PIME_WTICK(1)
                 if (q > 0) {
                     wait_d();                                               // P3 of the previous pass: Db = net.0
@@ -745,23 +874,26 @@ template <int KIND, int H> struct Engine {
                     epilogue_dot(row, half, H, (q - 1) & 1);                // net.2 (:158) of the previous pass
                     PIME_WTICK(3)
                 }
-                epilogue_l1i<1>(tid, g, ep & 1u);                           // lower rows; feeds integrator_net.2 (:155)
+                epilogue_l1i<1>(tid, g, e1buf);                             // lower rows; feeds integrator_net.2 (:155)
                 PIME_WTICK(4)
                 ++ep;
                 mbar_wait(l1b_rdy, (uint32_t)q & 1u);                       // Db = other_net.0 (:151)
                 tc_fence_after();
                 PIME_WTICK(5)
-                epilogue<>(row, half, H, ep & 1u);                          // tanh(Db) -> A, feeds other_net.2 (:152)
+                if constexpr (G::kTS) epilogue_ts<0, H / 64>(tid >> 5, H, ts_rdy);          // tanh(Db) in place, feeds other_net.2 (:152)
+                else epilogue<>(row, half, H, ep & 1u);
                 PIME_WTICK(6)
                 ++ep;
                 mbar_wait(h_rdy, (uint32_t)q & 1u);                         // P1: Da[0:H/2] = integrator_net.2 (complete long ago)
                 tc_fence_after();
                 PIME_WTICK(7)
-                epilogue<0, G::NP / 2>(row, half, 0, ep & 1u);              // first half of cat' (:170) while other_net.2 finishes
+                if constexpr (G::kTS) epilogue_ts<0, H / 128>(tid >> 5, 0, ts_rdy + kMaxChunks);   // first half of cat' (:170), in place
+                else epilogue<0, G::NP / 2>(row, half, 0, ep & 1u);
                 PIME_WTICK(8)
                 wait_d();                                                   // P2: Da[H/2:H] = other_net.2
                 PIME_WTICK(9)
-                epilogue<G::NP / 2, G::NP>(row, half, 0, ep & 1u);          // second half of cat', feeds net.0 (:157)
+                if constexpr (G::kTS) epilogue_ts<H / 128, H / 64>(tid >> 5, 0, ts_rdy + kMaxChunks);   // second half, feeds net.0 (:157)
+                else epilogue<G::NP / 2, G::NP>(row, half, 0, ep & 1u);
                 PIME_WTICK(10)
                 ++ep;
             }
