@@ -47,7 +47,7 @@ WORKLOADS = {
 FLOPS_PER_STEP = {("modular", 256, 4): 264704, ("modular", 128, 3): 66560, ("plain", 256, 30): 278016}  # 2 x weights, SURVEY 8a d4/d5
 TANH_PER_STEP = {("modular", 256, 4): 1025, ("modular", 128, 3): 513, ("plain", 256, 30): 769}
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (ncu --set full), keyed by (workload, envs, T); see profiles/
-NCU_DRAM_BYTES_PER_LAUNCH = {("wt", 1 << 20, 200): 6.7534e9}   # profiles/r02_ncu_summary.md (algorithmic: 6.71e9 replay rows)
+NCU_DRAM_BYTES_PER_LAUNCH = {("wt", 1 << 20, 200): 6.7555e9}   # profiles/r02_ncu_summary.md (algorithmic: 6.71e9 replay rows)
 NCU_DRAM_BYTES_STEP = {"wt": 1.8658e9, "ph": 2.2754e9}   # wt_step_vec4_kernel / ph_step_kernel<float>, 2^25 envs (algorithmic 1.913e9 / 2.315e9), profiles/r02_ncu_summary.md
 WT_STEP_BYTES_F32 = 57   # 36 B read + 21 B written per env-step, SoA fp32
 PH_STEP_BYTES_F32 = 69   # x, A, B are fp64 in the float flavour: read x8 r4 I4 A8 B8 C4 a4 t4 = 44, write x8 y4 I4 t4 rew4 done1 = 25
