@@ -50,7 +50,7 @@ constexpr int kWorkerThreads = 256;
 constexpr int kOwnerThreads = 128;
 constexpr int kThreads = 448;           // 8 worker warps + 4 owner warps + MMA warp + TMA warp
 constexpr int kMmaWarp = 12, kTmaWarp = 13;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 7;              // ring barriers reserved (Geo::Stages <= 7)
 constexpr int kMaxBlkBytes = 16384;
 constexpr int kChunkBytes = kRows * 16;    // one K core-matrix column (8 fp16) for all 128 rows = 2048 B
 constexpr int kK16Bytes = 2 * kChunkBytes; // one K=16 slice of an A operand = 4096 B
@@ -251,6 +251,7 @@ template <int KIND, int H> struct Geo {
     static constexpr int OnesOff = geo_ones_off(KIND, H);
     static constexpr int RingOff = OnesOff + kK16Bytes;
     static constexpr int Stages = kModular ? 5 : 7;
+    static_assert(Stages <= kMaxStages, "ring barriers");
     static constexpr int TblOff = RingOff + Stages * kMaxBlkBytes;
     static constexpr int OutWOff = TblOff + kMaxBlocks * 16;          // fp32 [H] + bias of the output layer
     static constexpr int PartOff = OutWOff + (H + 4) * 4;              // fp32 [2 groups][2 halves][128 rows] partial dot products
@@ -489,7 +490,7 @@ template <int KIND, int H> struct Engine {
         o_rdy = a_rdy + 2 * kMaxChunks;   // one set of piece barriers per A tile
         d_ready = o_rdy + 2;
         out_rdy = d_ready + 1;
-        h_rdy = out_rdy + 1;
+        h_rdy = out_rdy + 2;              // out_rdy[2]: one per group
         l1b_rdy = h_rdy + 1;
         p0_rdy = l1b_rdy + 1;
         ts_rdy = p0_rdy + 1;              // [2][kMaxChunks]: 64-column slabs of the two in-TMEM A operands (kTS)
@@ -505,7 +506,8 @@ template <int KIND, int H> struct Engine {
             mbar_init(&o_rdy[0], kOwnerThreads);
             mbar_init(&o_rdy[1], kOwnerThreads);
             mbar_init(d_ready, 1);
-            mbar_init(out_rdy, kWorkerThreads);
+            mbar_init(&out_rdy[0], kWorkerThreads);
+            mbar_init(&out_rdy[1], kWorkerThreads);
             mbar_init(h_rdy, 1);
             mbar_init(l1b_rdy, 1);
             mbar_init(p0_rdy, 1);
@@ -662,7 +664,7 @@ template <int KIND, int H> struct Engine {
                 // other_net.0 -> Db as soon as the owners have written the observation and the previous pass's last epilogue
                 // has read Db: it runs in the shadow of the CUDA-core epilogue of integrator_net.0.
                 mbar_wait(&o_rdy[g], ((uint32_t)q >> 1) & 1u);
-                if (q > 0) mbar_wait(out_rdy, ((uint32_t)q - 1u) & 1u);
+                if (q > 0) mbar_wait(&out_rdy[(q - 1) & 1], (((uint32_t)q - 1u) >> 1) & 1u);
                 tc_fence_after();
                 blk<H, true>(obs, 1, Db, l1b_rdy);
                 // P1: integrator_net.2 -> Da[0:H/2], once that epilogue has written its rows (all chunks arrive together).
@@ -694,7 +696,7 @@ template <int KIND, int H> struct Engine {
                     if (k == 0) blk<H, true>(obs, kk, X, x);
                     else blk<H, false>(obs + (uint32_t)k * kK16Bytes, kk, X, x);
                 }
-                if (q > 0) { mbar_wait(out_rdy, ((uint32_t)q - 1u) & 1u); tc_fence_after(); }   // last epilogue of the previous pass has read Y
+                if (q > 0) { mbar_wait(&out_rdy[(q - 1) & 1], (((uint32_t)q - 1u) >> 1) & 1u); tc_fence_after(); }   // last epilogue of the previous pass has read Y
                 layer<H>(Y, apar, 0u, 0, d_ready, nullptr);            // P1: net.2 -> Y
                 apar ^= 1;
                 layer<H>(X, apar, 0u, 0, d_ready, nullptr);            // P2: net.4 -> X; net.6 is the workers' dot product
@@ -820,7 +822,7 @@ template <int KIND, int H> struct Engine {
     }
 
     // Last layer: partial dot product over this thread's columns, sum_c act(D[:, c]) * w_out[c] in fp32; the two halves of
-    // a row meet in sPart[g][half][row], out_rdy collects all 256 workers (and tells the MMA warp that D is free again).
+    // a row meet in sPart[g][half][row], out_rdy[g] collects all 256 workers (and tells the MMA warp that D is free again).
     __device__ __forceinline__ void epilogue_dot(int row, int half, int dcol, int g) {
         const uint32_t taddr = tmem_base + ((uint32_t)((row / 32) * 32) << 16) + (uint32_t)(dcol + 16 * half);
         float v[2][16];
@@ -843,7 +845,7 @@ template <int KIND, int H> struct Engine {
         }
         sPart[(g * 2 + half) * kRows + row] = acc0 + acc1;
         tc_fence_before();   // the TMEM reads above are ordered before the MMAs that follow out_rdy
-        mbar_arrive(out_rdy);
+        mbar_arrive(&out_rdy[g]);
     }
 
     __device__ __forceinline__ void worker_loop(int passes) {
@@ -964,7 +966,11 @@ template <int KIND, int H> struct Engine {
     }
     // net(obs) of pass q for this row (pre-tanh, pre-prior): the two half-row partial sums + the output bias
     __device__ __forceinline__ float read_out(int row, int q) {
-        mbar_wait(out_rdy, (uint32_t)q & 1u);
+        // One barrier per group: the owner of group g cannot miss a phase of out_rdy[g] -- its next completion needs the
+        // observation this very thread writes after the wait.  (With a single barrier for both groups a short pass of the
+        // OTHER group, H = 32, could complete between this thread's write_obs and this wait: two phases ahead, the parity
+        // test reads "not yet" for ever.)
+        mbar_wait(&out_rdy[q & 1], ((uint32_t)q >> 1) & 1u);
         const int g = q & 1;
         return sPart[(g * 2) * kRows + row] + sPart[(g * 2 + 1) * kRows + row] + sOutW[H];
     }
