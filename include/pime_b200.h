@@ -305,6 +305,7 @@ int pime_wt_rollout_host_f32(const pime_wt_config *cfg, int64_t n, const pime_wt
 int pime_ph_rollout_host_f32(const pime_ph_config *cfg, const float *table, int64_t n, const pime_ph_state *st_host,
                              const pime_ph_state *st_dev, const pime_rollout_args *args, float *ep_return_host, void *stream);
 int pime_set_host_slices(int32_t slices);
+int pime_host_slice_plan(int64_t n, int32_t single, int64_t *out2); /* {slices, envs per slice} the entries would use */
 
 /* ---------------------------------------------------------------------------------------------------------
  * PPO learner: one minibatch step of AgentPPO.update_net (elegantrl/agent.py:635-658) on the GPU-resident replay

@@ -32,6 +32,16 @@ extern "C" int pime_wt_rollout_host_f32(const pime_wt_config *cfg, int64_t n, co
     return host_pipelined_rollout(n, arr, 9, (float *)d->ep_return, ep_return_host, args, (cudaStream_t)stream, launch, single);
 }
 
+// the slicing the host-buffer entries would use for n envs on the current device (148 SMs assumed when there is none):
+// out2 = {number of slices, envs per slice}.  Host arithmetic only.
+extern "C" int pime_host_slice_plan(int64_t n, int32_t single, int64_t *out2) {
+    PIME_REQUIRE(out2 && n >= 0, "null output / negative n");
+    const int slices = n == 0 ? 1 : host_slice_count(n, single != 0);
+    out2[0] = slices;
+    out2[1] = host_slice_len(n, slices);
+    return PIME_OK;
+}
+
 // tests / tuning: force the number of env slices of the host-buffer entries (0 = automatic)
 extern "C" int pime_set_host_slices(int32_t slices) {
     PIME_REQUIRE(slices >= 0 && slices <= kMaxSlices, "0 <= slices <= 8");

@@ -192,3 +192,31 @@ def test_ppo_learner_layout_is_host_computable(L, kind, S, H):
         assert L.lib().pime_ppo_work_floats(C.byref(cfg), C.c_int32(B)) == B * (32 + 2 * la + 2)
     bad = L.ActorConfig(kind=kind, state_dim=S, mid_dim=48, integrator_dim=1 if kind == 1 else 0)
     assert L.lib().pime_ppo_theta_count(C.byref(bad)) == -1
+
+
+def test_host_entry_slice_plan(L):
+    """csrc/host_pipe.cuh: the host-buffer entries cut large env ranges into <= 8 slices of whole waves (148 SMs x 256 envs);
+    small ranges, stacking frames (single = 1) and n = 0 stay in one piece; a forced count slices by whole 256-env tiles."""
+    lib = L.lib()
+    wave = 148 * 256
+
+    def plan(n, single=0):
+        out = (C.c_int64 * 2)()
+        assert lib.pime_host_slice_plan(C.c_int64(n), C.c_int32(single), out) == 0
+        return int(out[0]), int(out[1])
+
+    assert plan(0) == (1, 0) and plan(1000) == (1, 1000) and plan(8 * wave - 1) == (1, 8 * wave - 1)
+    assert plan(8 * wave) == (2, 4 * wave)
+    assert plan(1 << 20) == (6, 5 * wave)                       # BASELINE configs[2]: 5 x 5 waves + 2.7 waves
+    s, ln = plan(1 << 23)                                       # configs[3] on one GPU
+    assert s == 8 and ln % wave == 0 and (s - 1) * ln < (1 << 23) <= s * ln
+    assert plan(1 << 23, single=1) == (1, 1 << 23)
+    for n in (wave * 9 + 5, 3 * (1 << 20) + 17, 1 << 25):
+        s, ln = plan(n)
+        assert 1 <= s <= 8 and ln % wave == 0 and (s - 1) * ln < n <= s * ln and ln >= 4 * wave
+    assert lib.pime_set_host_slices(3) == 0
+    try:
+        assert plan(1000) == (3, 512) and plan(300) == (2, 256) and plan(100) == (1, 100)
+    finally:
+        assert lib.pime_set_host_slices(0) == 0
+    assert lib.pime_set_host_slices(9) != 0
